@@ -1,0 +1,321 @@
+"""ctypes binding of include/sf3d.h.
+
+`SoilFluxes3D(path)` loads ONE implementation of the C ABI and exposes it under the
+reference's own function names (agrolib/soilFluxes3D/soilFluxes3D.h:9-104), so harness and
+test code reads like a caller of the reference plugin API:
+
+    sf = SoilFluxes3D(PRODUCT_LIB)
+    sf.initializeSF3D(nrNodes, nrSurface, 8, True, False, False)
+    sf.setNode(i, x, y, z, area, True, BoundaryType.Runoff, slope, width)
+    dt = sf.computeStep(3600.0)
+
+Three libraries implement the ABI (see include/sf3d.h): the CUDA product, the CPU
+restatement (oracle/) and the unmodified reference (oracle/_ref/).  This module is plumbing
+only; it never chooses an implementation on behalf of the caller and has no fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import os
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+PRODUCT_LIB = ROOT / "criteria3d_b200" / "libsf3d_b200.so"
+ORACLE_LIB = ROOT / "oracle" / "libsf3d_oracle.so"
+REFERENCE_LIB = ROOT / "oracle" / "_ref" / "libsf3d_ref.so"
+
+
+class SF3Derror(enum.IntEnum):  # types.h:39-40
+    SF3Dok = 0
+    IndexError = 1
+    MemoryError = 2
+    TopographyError = 3
+    BoundaryError = 4
+    MissingDataError = 5
+    ParameterError = 6
+    SolverError = 7
+    FileError = 8
+
+
+class BoundaryType(enum.IntEnum):  # types.h:98-99
+    NoBoundary = 0
+    Runoff = 1
+    FreeDrainage = 2
+    FreeLateralDrainage = 3
+    PrescribedTotalWaterPotential = 4
+    Urban = 5
+    Road = 6
+    Culvert = 7
+    HeatSurface = 8
+    SoluteFlux = 9
+
+
+class LinkType(enum.IntEnum):  # types.h:101
+    NoLink = 0
+    Up = 1
+    Down = 2
+    Lateral = 3
+
+
+class WRCModel(enum.IntEnum):  # types.h:135
+    VanGenuchten = 0
+    ModifiedVanGenuchten = 1
+    Campbell = 2
+
+
+class MeanType(enum.IntEnum):  # types.h:36
+    Arithmetic = 0
+    Geometric = 1
+    Logarithmic = 2
+
+
+class HeatFluxSaveMode(enum.IntEnum):  # types.h:186
+    None_ = 0
+    Total = 1
+    All = 2
+
+
+class FluxType(enum.IntEnum):  # types.h:199
+    HeatTotal = 0
+    HeatDiffusive = 1
+    HeatLatentIsothermal = 2
+    HeatLatentThermal = 3
+    HeatAdvective = 4
+    WaterLiquidIsothermal = 5
+    WaterLiquidThermal = 6
+    WaterVaporIsothermal = 7
+    WaterVaporThermal = 8
+
+
+class Field(enum.IntEnum):  # include/sf3d.h enum sf3d_field
+    WATER_CONTENT = 0
+    DEGREE_OF_SATURATION = 1
+    WATER_CONDUCTIVITY = 2
+    MATRIC_POTENTIAL = 3
+    TOTAL_POTENTIAL = 4
+    POND = 5
+    WATER_SINK_SOURCE = 6
+    BOUNDARY_WATER_FLOW = 7
+    PRESCRIBED_POTENTIAL = 8
+    TEMPERATURE = 9
+    HEAT_SINK_SOURCE = 10
+    SUM_LATERAL_FLOW = 11
+    MAX_FLOW_UP = 12
+    MAX_FLOW_DOWN = 13
+    MAX_FLOW_LATERAL = 14
+    HEAT_CONDUCTIVITY = 15
+    BOUNDARY_NET_IRRADIANCE = 16
+    BOUNDARY_TEMPERATURE = 17
+    BOUNDARY_RELATIVE_HUMIDITY = 18
+    BOUNDARY_WIND_SPEED = 19
+
+
+# sentinel doubles of getDoubleErrorValue (types.h:42-64)
+INDEX_ERROR = -1111.0
+MEMORY_ERROR = -2222.0
+TOPOGRAPHY_ERROR = -3333.0
+BOUNDARY_ERROR = -4444.0
+MISSING_DATA_ERROR = -9999.0
+PARAMETER_ERROR = -7777.0
+NODATA = -9999.0
+
+
+class GridDesc(C.Structure):
+    _fields_ = [
+        ("rows", C.c_uint32), ("cols", C.c_uint32), ("layers", C.c_uint32), ("n_valid", C.c_uint32),
+        ("cell", C.c_double), ("x_ll", C.c_double), ("y_ll", C.c_double),
+        ("dem", C.POINTER(C.c_float)), ("slope_tan", C.POINTER(C.c_float)),
+        ("cell_rank", C.POINTER(C.c_int32)), ("outlet", C.POINTER(C.c_uint8)),
+        ("soil_id", C.POINTER(C.c_uint16)), ("surface_id", C.POINTER(C.c_uint16)),
+        ("pond", C.POINTER(C.c_double)),
+        ("layer_depth", C.POINTER(C.c_double)), ("layer_thickness", C.POINTER(C.c_double)),
+        ("layer_horizon", C.POINTER(C.c_uint16)), ("boundary_l1", C.POINTER(C.c_uint8)),
+        ("free_catchment_runoff", C.c_int), ("free_lateral_drainage", C.c_int),
+        ("free_bottom_drainage", C.c_int),
+    ]
+
+
+class Counters(C.Structure):
+    _fields_ = [
+        ("steps", C.c_uint64), ("tries", C.c_uint64), ("approximations", C.c_uint64),
+        ("sweeps", C.c_uint64), ("heat_steps", C.c_uint64), ("heat_sweeps", C.c_uint64),
+        ("kernel_launches", C.c_uint64),
+        ("delta_t_curr", C.c_double), ("last_courant", C.c_double),
+        ("last_mbr", C.c_double), ("last_mbe", C.c_double),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+u8, u16, u32, dbl, cint = C.c_uint8, C.c_uint16, C.c_uint32, C.c_double, C.c_int
+
+# (C symbol, reference name, restype, argtypes) -- one row per soilFluxes3D.h declaration
+_API = [
+    ("sf3d_initialize", "initializeSF3D", u8, [u32, u32, u8, cint, cint, cint, u8]),
+    ("sf3d_initialize_balance", "initializeBalance", u8, []),
+    ("sf3d_clean", "cleanSF3D", u8, []),
+    ("sf3d_initialize_heat_flag", "initializeHeatFlag", u8, [u8, cint, cint]),
+    ("sf3d_set_threads_number", "setThreadsNumber", u32, [u32]),
+    ("sf3d_set_use_lineal", "setUseLineal", None, [cint]),
+    ("sf3d_set_lineal_method", "setLinealMethod", None, [cint]),
+    ("sf3d_set_soil_properties", "setSoilProperties", u8, [u16, u8] + [dbl] * 10),
+    ("sf3d_set_surface_properties", "setSurfaceProperties", u8, [u16, dbl]),
+    ("sf3d_set_numerical_parameters", "setNumericalParameters", u8, [dbl, dbl, u16, u16, u8, u8]),
+    ("sf3d_set_hydraulic_properties", "setHydraulicProperties", u8, [u8, u8, C.c_float]),
+    ("sf3d_set_culvert", "setCulvert", u8, [u32, dbl, dbl, dbl, dbl]),
+    ("sf3d_set_node", "setNode", u8, [u32, dbl, dbl, dbl, dbl, cint, u8, dbl, dbl]),
+    ("sf3d_set_node_link", "setNodeLink", u8, [u32, u32, u8, dbl]),
+    ("sf3d_set_node_boundary", "setNodeBoundary", u8, [u32, u8, dbl, dbl]),
+    ("sf3d_set_node_soil", "setNodeSoil", u8, [u32, u16, u16]),
+    ("sf3d_set_node_surface", "setNodeSurface", u8, [u32, u16]),
+    ("sf3d_set_node_pond", "setNodePond", u8, [u32, dbl]),
+    ("sf3d_set_node_water_content", "setNodeWaterContent", u8, [u32, dbl]),
+    ("sf3d_set_node_degree_of_saturation", "setNodeDegreeOfSaturation", u8, [u32, dbl]),
+    ("sf3d_set_node_matric_potential", "setNodeMatricPotential", u8, [u32, dbl]),
+    ("sf3d_set_node_total_potential", "setNodeTotalPotential", u8, [u32, dbl]),
+    ("sf3d_set_node_water_sink_source", "setNodeWaterSinkSource", u8, [u32, dbl]),
+    ("sf3d_set_node_prescribed_total_potential", "setNodePrescribedTotalPotential", u8, [u32, dbl]),
+    ("sf3d_get_node_water_content", "getNodeWaterContent", dbl, [u32]),
+    ("sf3d_get_node_maximum_water_content", "getNodeMaximumWaterContent", dbl, [u32]),
+    ("sf3d_get_node_minimum_water_content", "getNodeMinimumWaterContent", dbl, [u32]),
+    ("sf3d_get_node_available_water_content", "getNodeAvailableWaterContent", dbl, [u32]),
+    ("sf3d_get_node_water_deficit", "getNodeWaterDeficit", dbl, [u32, dbl]),
+    ("sf3d_get_node_degree_of_saturation", "getNodeDegreeOfSaturation", dbl, [u32]),
+    ("sf3d_get_node_water_conductivity", "getNodeWaterConductivity", dbl, [u32]),
+    ("sf3d_get_node_matric_potential", "getNodeMatricPotential", dbl, [u32]),
+    ("sf3d_get_node_total_potential", "getNodeTotalPotential", dbl, [u32]),
+    ("sf3d_get_node_pond", "getNodePond", dbl, [u32]),
+    ("sf3d_get_node_max_water_flow", "getNodeMaxWaterFlow", dbl, [u32, u8]),
+    ("sf3d_get_node_sum_lateral_water_flow", "getNodeSumLateralWaterFlow", dbl, [u32]),
+    ("sf3d_get_node_sum_lateral_water_flow_in", "getNodeSumLateralWaterFlowIn", dbl, [u32]),
+    ("sf3d_get_node_sum_lateral_water_flow_out", "getNodeSumLateralWaterFlowOut", dbl, [u32]),
+    ("sf3d_get_node_boundary_water_flow", "getNodeBoundaryWaterFlow", dbl, [u32]),
+    ("sf3d_get_total_boundary_water_flow", "getTotalBoundaryWaterFlow", dbl, [u8]),
+    ("sf3d_get_total_water_content", "getTotalWaterContent", dbl, []),
+    ("sf3d_get_water_storage", "getWaterStorage", dbl, []),
+    ("sf3d_get_water_mbr", "getWaterMBR", dbl, []),
+    ("sf3d_set_node_heat_sink_source", "setNodeHeatSinkSource", u8, [u32, dbl]),
+    ("sf3d_set_node_temperature", "setNodeTemperature", u8, [u32, dbl]),
+    ("sf3d_set_node_boundary_fixed_temperature", "setNodeBoundaryFixedTemperature", u8, [u32, dbl, dbl]),
+    ("sf3d_set_node_boundary_height_wind", "setNodeBoundaryHeightWind", u8, [u32, dbl]),
+    ("sf3d_set_node_boundary_height_temperature", "setNodeBoundaryHeightTemperature", u8, [u32, dbl]),
+    ("sf3d_set_node_boundary_net_irradiance", "setNodeBoundaryNetIrradiance", u8, [u32, dbl]),
+    ("sf3d_set_node_boundary_temperature", "setNodeBoundaryTemperature", u8, [u32, dbl]),
+    ("sf3d_set_node_boundary_relative_humidity", "setNodeBoundaryRelativeHumidity", u8, [u32, dbl]),
+    ("sf3d_set_node_boundary_roughness", "setNodeBoundaryRoughness", u8, [u32, dbl]),
+    ("sf3d_set_node_boundary_wind_speed", "setNodeBoundaryWindSpeed", u8, [u32, dbl]),
+    ("sf3d_get_node_temperature", "getNodeTemperature", dbl, [u32]),
+    ("sf3d_get_node_heat_conductivity", "getNodeHeatConductivity", dbl, [u32]),
+    ("sf3d_get_node_vapor", "getNodeVapor", dbl, [u32]),
+    ("sf3d_get_node_heat_storage", "getNodeHeatStorage", dbl, [u32, dbl]),
+    ("sf3d_get_node_heat_max_flux", "getNodeHeatMaxFlux", dbl, [u32, u8, u8]),
+    ("sf3d_get_node_boundary_advective_flux", "getNodeBoundaryAdvectiveFlux", dbl, [u32]),
+    ("sf3d_get_node_boundary_latent_flux", "getNodeBoundaryLatentFlux", dbl, [u32]),
+    ("sf3d_get_node_boundary_radiative_flux", "getNodeBoundaryRadiativeFlux", dbl, [u32]),
+    ("sf3d_get_node_boundary_sensible_flux", "getNodeBoundarySensibleFlux", dbl, [u32]),
+    ("sf3d_get_node_boundary_aerodynamic_conductance", "getNodeBoundaryAerodynamicConductance", dbl, [u32]),
+    ("sf3d_get_node_boundary_soil_conductance", "getNodeBoundarySoilConductance", dbl, [u32]),
+    ("sf3d_get_heat_mbr", "getHeatMBR", dbl, []),
+    ("sf3d_get_heat_mbe", "getHeatMBE", dbl, []),
+    ("sf3d_compute_period", "computePeriod", None, [dbl]),
+    ("sf3d_compute_step", "computeStep", dbl, [dbl]),
+]
+
+_EXT = [
+    ("sf3d_ext_get_field", u8, [cint, u32, u32, C.POINTER(dbl)]),
+    ("sf3d_ext_set_field", u8, [cint, u32, u32, C.POINTER(dbl)]),
+    ("sf3d_ext_get_link_table", u8, [u8, u32, u32, C.POINTER(u8), C.POINTER(u32), C.POINTER(dbl)]),
+    ("sf3d_ext_get_node_meta", u8, [u32, u32, C.POINTER(u8), C.POINTER(u8), C.POINTER(u8)]),
+    ("sf3d_ext_build_grid", u8, [C.POINTER(GridDesc)]),
+    ("sf3d_ext_get_counters", u8, [C.POINTER(Counters)]),
+    ("sf3d_ext_reset_counters", u8, []),
+    ("sf3d_ext_backend", C.c_char_p, []),
+    ("sf3d_ext_set_device", u8, [cint]),
+]
+
+ALL_SYMBOLS = [s for s, *_ in _API] + [s for s, *_ in _EXT]
+
+
+def _ptr(a: np.ndarray, ctype):
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+class SoilFluxes3D:
+    """One loaded implementation of the sf3d C ABI, under the reference's function names."""
+
+    def __init__(self, path: os.PathLike | str):
+        path = Path(path)
+        if not path.exists():
+            raise FileNotFoundError(
+                f"{path} not found: build it first (python -c 'import __graft_entry__ as g; g.build()')")
+        self.path = path
+        self.lib = C.CDLL(str(path), mode=C.RTLD_LOCAL)
+        for sym, name, res, args in _API:
+            fn = getattr(self.lib, sym)
+            fn.restype, fn.argtypes = res, args
+            setattr(self, name, fn)
+        for sym, res, args in _EXT:
+            fn = getattr(self.lib, sym)
+            fn.restype, fn.argtypes = res, args
+        self.backend = self.lib.sf3d_ext_backend().decode()
+
+    # ---- bulk extensions ---------------------------------------------------------
+    def get_field(self, field: Field, first: int, count: int, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty(count, dtype=np.float64)
+        assert out.dtype == np.float64 and out.flags.c_contiguous and out.size >= count
+        rc = self.lib.sf3d_ext_get_field(int(field), first, count, _ptr(out, dbl))
+        if rc:
+            raise RuntimeError(f"sf3d_ext_get_field({field!r}) -> {SF3Derror(rc).name}")
+        return out
+
+    def set_field(self, field: Field, first: int, values: np.ndarray) -> int:
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        return self.lib.sf3d_ext_set_field(int(field), first, v.size, _ptr(v, dbl))
+
+    def link_table(self, slot: int, first: int, count: int):
+        lt = np.empty(count, np.uint8)
+        li = np.empty(count, np.uint32)
+        ar = np.empty(count, np.float64)
+        rc = self.lib.sf3d_ext_get_link_table(slot, first, count, _ptr(lt, u8), _ptr(li, u32), _ptr(ar, dbl))
+        if rc:
+            raise RuntimeError(f"sf3d_ext_get_link_table -> {SF3Derror(rc).name}")
+        return lt, li, ar
+
+    def node_meta(self, first: int, count: int):
+        sfl = np.empty(count, np.uint8)
+        bt = np.empty(count, np.uint8)
+        nl = np.empty(count, np.uint8)
+        rc = self.lib.sf3d_ext_get_node_meta(first, count, _ptr(sfl, u8), _ptr(bt, u8), _ptr(nl, u8))
+        if rc:
+            raise RuntimeError(f"sf3d_ext_get_node_meta -> {SF3Derror(rc).name}")
+        return sfl, bt, nl
+
+    def build_grid(self, desc: GridDesc) -> int:
+        return self.lib.sf3d_ext_build_grid(C.byref(desc))
+
+    def counters(self) -> dict:
+        c = Counters()
+        rc = self.lib.sf3d_ext_get_counters(C.byref(c))
+        if rc:
+            raise RuntimeError(f"sf3d_ext_get_counters -> {SF3Derror(rc).name}")
+        return c.as_dict()
+
+    def reset_counters(self) -> None:
+        self.lib.sf3d_ext_reset_counters()
+
+    def set_device(self, device: int) -> int:
+        return self.lib.sf3d_ext_set_device(device)
+
+
+def load_product() -> SoilFluxes3D:
+    """The CUDA product.  Fails loudly when the library is missing: there is no fallback."""
+    if not PRODUCT_LIB.exists():
+        raise RuntimeError(
+            f"{PRODUCT_LIB} is missing. The B200 product is CUDA only (no CPU fallback): "
+            "run `python -c 'import __graft_entry__ as g; g.build()'` first.")
+    return SoilFluxes3D(PRODUCT_LIB)
