@@ -144,11 +144,18 @@ class Counters(C.Structure):
         ("sweeps", C.c_uint64), ("heat_steps", C.c_uint64), ("heat_sweeps", C.c_uint64),
         ("kernel_launches", C.c_uint64),
         ("delta_t_curr", C.c_double), ("last_courant", C.c_double),
-        ("last_mbr", C.c_double), ("last_mbe", C.c_double),
+        ("last_mbr", C.c_double), ("last_mbe", C.c_double), ("links", C.c_uint64),
     ]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+KERNEL_NAMES = ["begin_try", "node_phase", "assemble", "jacobi", "post", "accept", "other"]
+
+
+class KernelTimes(C.Structure):
+    _fields_ = [("ms", C.c_double * 7), ("launches", C.c_uint64 * 7)]
 
 
 u8, u16, u32, dbl, cint = C.c_uint8, C.c_uint16, C.c_uint32, C.c_double, C.c_int
@@ -235,6 +242,10 @@ _EXT = [
     ("sf3d_ext_reset_counters", u8, []),
     ("sf3d_ext_backend", C.c_char_p, []),
     ("sf3d_ext_set_device", u8, [cint]),
+    ("sf3d_ext_reset_solver", u8, []),
+    ("sf3d_ext_stream", C.c_void_p, []),
+    ("sf3d_ext_profile", u8, [cint]),
+    ("sf3d_ext_get_kernel_times", u8, [C.POINTER(KernelTimes)]),
 ]
 
 ALL_SYMBOLS = [s for s, *_ in _API] + [s for s, *_ in _EXT]
@@ -310,6 +321,22 @@ class SoilFluxes3D:
 
     def set_device(self, device: int) -> int:
         return self.lib.sf3d_ext_set_device(device)
+
+    def reset_solver(self) -> int:
+        return self.lib.sf3d_ext_reset_solver()
+
+    def stream(self) -> int | None:
+        return self.lib.sf3d_ext_stream()
+
+    def profile(self, enable: bool) -> int:
+        return self.lib.sf3d_ext_profile(1 if enable else 0)
+
+    def kernel_times(self) -> dict:
+        kt = KernelTimes()
+        rc = self.lib.sf3d_ext_get_kernel_times(C.byref(kt))
+        if rc:
+            raise RuntimeError(f"sf3d_ext_get_kernel_times -> {SF3Derror(rc).name}")
+        return {n: {"ms": kt.ms[i], "launches": int(kt.launches[i])} for i, n in enumerate(KERNEL_NAMES)}
 
 
 def load_product() -> SoilFluxes3D:

@@ -1,0 +1,69 @@
+// sf3d_backend.h -- the device-side services the host engine uses: memory, copies and one
+// launcher per kernel.  Implemented in sf3d_kernels.cu (CUDA, sm_100a).  There is exactly one
+// implementation; if CUDA is unavailable every entry point throws (no CPU fallback).
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+#include "sf3d_view.h"
+#include "sf3d.h"
+
+namespace sf3d {
+
+struct DeviceError { int code; const char *what; const char *where; };
+
+// ---- memory / transfers (all on the library's stream) ------------------------------------
+void   dev_select(int device);          // cudaSetDevice + stream creation (idempotent)
+int    dev_current();
+void  *dev_alloc(size_t bytes);          // cudaMalloc + zero fill (reference uses calloc)
+void   dev_free(void *p);
+void   dev_zero(void *p, size_t bytes);
+void   dev_fill_f64(double *p, size_t n, double value);
+void   dev_copy(void *dst, const void *src, size_t bytes);      // device to device
+void   h2d(void *dst, const void *src, size_t bytes);
+void   d2h(void *dst, const void *src, size_t bytes);
+void  *pinned_alloc(size_t bytes);
+void   pinned_free(void *p);
+void   dev_sync();
+uint64_t launches();                     // kernels launched by this library so far
+void  *dev_stream();                     // cudaStream_t of the library (for event timing)
+void   prof_enable(bool on);             // CUDA-event timing of every launch, per kernel kind
+void   prof_get(double ms[SF3D_K_COUNT], uint64_t n[SF3D_K_COUNT]);
+uint64_t k_count_links(const SF3DView &v);
+
+// ---- kernels -----------------------------------------------------------------------------
+int  reduce_blocks(uint32_t n);          // grid size used by all reducing kernels for n rows
+void k_link_geometry(const SF3DView &v, int *surfaceOrderOk);
+void k_begin_try(const SF3DView &v);
+void k_restore_old(const SF3DView &v);
+void k_node_phase(const SF3DView &v, double dt, int withCapacity);
+void k_assemble(const SF3DView &v, double dt, int approx, double dtMin);
+void k_jacobi(const SF3DView &v, const double *xin, double *xout, int maxIter, double tol);
+void k_post(const SF3DView &v, const double *x, double dt, int mode);
+void k_accept(const SF3DView &v, double dt);
+void k_restore_best(const SF3DView &v);
+void k_total_boundary_flow(const SF3DView &v, uint32_t boundaryType);
+void read_ctrl(const SF3DView &v, Ctrl *out);     // async copy to pinned + stream sync
+void write_ctrl(const SF3DView &v, const Ctrl *in);
+
+// bulk field access (device kernels; first/count in nodes)
+void k_set_potential(const SF3DView &v, uint32_t first, uint32_t count, const double *src, int isTotal);
+void k_get_field(const SF3DView &v, int field, uint32_t first, uint32_t count, double *dst);
+
+// device-side DEM -> graph builder (sf3d_ext_build_grid)
+struct GridDev {
+    uint32_t rows, cols, layers, nValid;
+    double cell, xll, yll;
+    const float *dem, *slope;
+    const int32_t *rank;
+    const uint8_t *outlet, *boundaryL1;
+    const uint16_t *soilId, *surfaceId;
+    const double *pond;
+    const double *layerDepth, *layerThickness;
+    const uint16_t *layerTab;       // [layers * nSoilIds]: soil-table row of (soil id, layer horizon)
+    uint32_t nSoilIds;
+    int freeRunoff, freeLateral, freeBottom;
+    int computeWater, computeHeat;
+};
+void k_build_grid(const SF3DView &v, const GridDev &g);
+
+}  // namespace sf3d

@@ -1,0 +1,949 @@
+// sf3d_capi.cpp -- the C ABI of include/sf3d.h for the B200 product.
+//
+// Role: the reference's soilFluxes3D.cpp (global nodeGrid + scalar setters/getters) with the
+// state living in HBM.  Scalar setters/getters work on lazily allocated host mirrors; a mirror
+// is pushed to the device in one copy before the next kernel needs it and pulled in one copy
+// the first time a getter asks after the device changed it.  Bulk extensions move
+// whole ranges and never allocate host mirrors.  Validation and return codes follow the
+// reference function of the same name (file:line cited at each function).
+#include <float.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <thread>
+#include <vector>
+#include "sf3d.h"
+#include "sf3d_engine.h"
+#include "sf3d_rows_heat.h"
+
+using namespace sf3d;
+
+namespace {
+
+template <class T>
+struct Mirror {
+    T *d = nullptr;
+    T *h = nullptr;
+    size_t n = 0;
+    bool hostNewer = false, devNewer = false;
+
+    void alloc(size_t count) { n = count; d = (T *)dev_alloc(count * sizeof(T)); }
+    void release() { dev_free(d); free(h); d = h = nullptr; n = 0; hostNewer = devNewer = false; }
+    T *sync_host()
+    {
+        if (!h) { h = (T *)calloc(n ? n : 1, sizeof(T)); if (!h) throw DeviceError{-2, "host alloc", "Mirror"}; }
+        if (devNewer) { d2h(h, d, n * sizeof(T)); devNewer = false; }
+        return h;
+    }
+    const T *ro() { return sync_host(); }
+    T *rw() { T *p = sync_host(); hostNewer = true; return p; }
+    void push() { if (hostNewer) { h2d(d, h, n * sizeof(T)); hostNewer = false; } }
+    void dev_written() { devNewer = true; }     // call after push()
+};
+
+struct State {
+    bool initialized = false;
+    bool water = true, heat = false, solutes = false, heatVapor = false, heatAdvection = false;
+    uint8_t hfMode = 0;
+    uint32_t N = 0, Ns = 0;
+
+    std::vector<SoilRec> soils;
+    std::vector<std::pair<uint16_t, uint8_t>> soilKeys;   // (soilNumber, horizonNumber) of each record
+    std::vector<std::vector<uint16_t>> soil1D;
+    std::vector<double> rough;
+    std::vector<CulvertRec> culverts;
+    bool tablesDirty = true, topoDirty = true;
+    SoilRec *dSoil = nullptr; double *dRough = nullptr; CulvertRec *dCulv = nullptr;
+    size_t dSoilCap = 0, dRoughCap = 0, dCulvCap = 0;
+
+    Mirror<double> x, y, z, size, bSlope, bSize, bRate, bSum, bPresc;
+    Mirror<uint32_t> meta, lidx, culvertOf;
+    Mirror<uint16_t> tab;
+    Mirror<double> larea, lflow;
+    Mirror<double> H, oldH, Se, K, sink, pond;
+    // device-only
+    double *bestH = nullptr, *SeOld = nullptr, *wFlow = nullptr, *ldist = nullptr, *mval = nullptr,
+           *b = nullptr, *cap = nullptr, *x0 = nullptr, *x1 = nullptr, *partA = nullptr, *partB = nullptr,
+           *partC = nullptr, *scratch = nullptr;
+    uint32_t *mcol = nullptr;
+    Ctrl *ctrl = nullptr;
+
+    Engine eng;
+};
+
+State S;
+SolverParams g_params = default_params();       // survives cleanSF3D like the global CPUSolverObject
+bool g_useLineal = false; int g_linealMethod = 0;
+int g_device = 0;
+
+double err_value(uint8_t code)                     // getDoubleErrorValue, types.h:42-64
+{
+    switch (code)
+    {
+        case SF3D_OK: return 0;
+        case SF3D_INDEX_ERROR: return -1111;
+        case SF3D_MEMORY_ERROR: return -2222;
+        case SF3D_TOPOGRAPHY_ERROR: return -3333;
+        case SF3D_BOUNDARY_ERROR: return -4444;
+        case SF3D_MISSING_DATA_ERROR: return -9999;
+        case SF3D_PARAMETER_ERROR: return -7777;
+        default: return -1111;
+    }
+}
+
+void fill_view()
+{
+    SF3DView &v = S.eng.v;
+    memset(&v, 0, sizeof v);
+    v.N = S.N; v.Ns = S.Ns;
+    v.computeHeat = S.heat; v.computeHeatVapor = S.heatVapor; v.computeHeatAdvection = S.heatAdvection;
+    v.hfSaveMode = S.hfMode;
+    v.wrcModel = g_params.wrcModel; v.meanType = g_params.meanType;
+    v.lvRatio = g_params.lateralVerticalRatio; v.heatWF = g_params.heatWeightFactor;
+    v.x = S.x.d; v.y = S.y.d; v.z = S.z.d; v.size = S.size.d; v.meta = S.meta.d; v.tab = S.tab.d;
+    v.bSlope = S.bSlope.d; v.bSize = S.bSize.d; v.bRate = S.bRate.d; v.bSum = S.bSum.d; v.bPresc = S.bPresc.d;
+    v.lidx = S.lidx.d; v.larea = S.larea.d; v.lflow = S.lflow.d; v.ldist = S.ldist;
+    v.H = S.H.d; v.oldH = S.oldH.d; v.bestH = S.bestH; v.Se = S.Se.d; v.SeOld = S.SeOld; v.K = S.K.d;
+    v.wFlow = S.wFlow; v.sink = S.sink.d; v.pond = S.pond.d; v.inv = nullptr;
+    v.mcol = S.mcol; v.mval = S.mval; v.b = S.b; v.cap = S.cap; v.x0 = S.x0; v.x1 = S.x1;
+    v.soil = S.dSoil; v.rough = S.dRough;
+    v.culverts = S.culverts.empty() ? nullptr : S.dCulv;
+    v.culvertOf = S.culverts.empty() ? nullptr : S.culvertOf.d;
+    v.ctrl = S.ctrl; v.partA = S.partA; v.partB = S.partB; v.partC = S.partC;
+}
+
+void upload_tables()
+{
+    if (!S.tablesDirty) return;
+    if (S.soils.size() > S.dSoilCap)
+    {
+        dev_free(S.dSoil);
+        S.dSoilCap = std::max<size_t>(64, S.soils.size() * 2);
+        S.dSoil = (SoilRec *)dev_alloc(S.dSoilCap * sizeof(SoilRec));
+    }
+    if (!S.soils.empty()) h2d(S.dSoil, S.soils.data(), S.soils.size() * sizeof(SoilRec));
+    if (S.rough.size() > S.dRoughCap)
+    {
+        dev_free(S.dRough);
+        S.dRoughCap = std::max<size_t>(64, S.rough.size() * 2);
+        S.dRough = (double *)dev_alloc(S.dRoughCap * sizeof(double));
+    }
+    if (!S.rough.empty()) h2d(S.dRough, S.rough.data(), S.rough.size() * sizeof(double));
+    if (S.culverts.size() > S.dCulvCap)
+    {
+        dev_free(S.dCulv);
+        S.dCulvCap = std::max<size_t>(16, S.culverts.size() * 2);
+        S.dCulv = (CulvertRec *)dev_alloc(S.dCulvCap * sizeof(CulvertRec));
+    }
+    if (!S.culverts.empty()) h2d(S.dCulv, S.culverts.data(), S.culverts.size() * sizeof(CulvertRec));
+    S.tablesDirty = false;
+}
+
+// everything the kernels read must be current on the device
+uint8_t sync_to_device(bool finalizeTopology = true)
+{
+    upload_tables();
+    S.x.push(); S.y.push(); S.z.push(); S.size.push(); S.meta.push(); S.tab.push();
+    S.bSlope.push(); S.bSize.push(); S.bRate.push(); S.bSum.push(); S.bPresc.push();
+    S.lidx.push(); S.larea.push(); S.lflow.push(); S.culvertOf.push();
+    S.H.push(); S.oldH.push(); S.Se.push(); S.K.push(); S.sink.push(); S.pond.push();
+    fill_view();
+    if (S.topoDirty && finalizeTopology)
+    {
+        int ok = 1;
+        k_link_geometry(S.eng.v, &ok);
+        S.topoDirty = false;
+        if (!ok)
+        {
+            fprintf(stderr, "[sf3d_b200] topology error: surface nodes must occupy indices [0, nrSurfaceNodes) "
+                            "(the reference solver assumes it: cpusolver.cpp:151,166,413,426)\n");
+            return SF3D_TOPOGRAPHY_ERROR;
+        }
+    }
+    return SF3D_OK;
+}
+
+void step_wrote_device()
+{
+    S.H.dev_written(); S.oldH.dev_written(); S.Se.dev_written(); S.K.dev_written();
+    S.bRate.dev_written(); S.bSum.dev_written(); S.lflow.dev_written();
+}
+
+// host-side physics for the scalar setters (same row functions, compiled for the host)
+double host_se_from_theta(const SoilRec &s, double theta)          // soilPhysics.cpp:123-134
+{
+    if (theta >= s.thetaS) return 1.;
+    if (theta < s.thetaR) return 0.;
+    return (theta - s.thetaR) / (s.thetaS - s.thetaR);
+}
+double host_psi_from_se(const SoilRec &s, double Se)               // Soil::computeNodePsi, soilPhysics.cpp:141-158
+{
+    double temp;
+    if (g_params.wrcModel == 0) temp = pow(1. / Se, 1. / s.m) - 1.;
+    else if (g_params.wrcModel == 1) temp = pow(1. / (Se * s.Sc), 1. / s.m) - 1;
+    else return SF3D_NODATA;
+    return (1. / s.alpha) * pow(temp, 1. / s.n);
+}
+const SoilRec &node_soil(uint32_t i) { return S.soils[S.tab.ro()[i]]; }
+bool is_surface(uint32_t i) { return META_SURFACE(S.meta.ro()[i]) != 0; }
+uint32_t node_bt(uint32_t i) { return META_BT(S.meta.ro()[i]); }
+double host_node_K(uint32_t i, double Se) { return sf3d_mualem(node_soil(i), g_params.wrcModel, Se); }
+
+#define REQUIRE_INIT_E()  do { if (!S.initialized) return SF3D_MEMORY_ERROR; } while (0)
+#define REQUIRE_INDEX_E(i) do { if ((i) >= S.N) return SF3D_INDEX_ERROR; } while (0)
+#define REQUIRE_INIT_D()  do { if (!S.initialized) return err_value(SF3D_MEMORY_ERROR); } while (0)
+#define REQUIRE_INDEX_D(i) do { if ((i) >= S.N) return err_value(SF3D_INDEX_ERROR); } while (0)
+
+template <class F>
+auto guarded(F &&f, decltype(f()) onError) -> decltype(f())
+{
+    try { return f(); }
+    catch (const DeviceError &e)
+    {
+        fprintf(stderr, "[sf3d_b200] device error in %s: %s\n", e.where, e.what);
+        return onError;
+    }
+}
+
+void release_all()
+{
+    S.x.release(); S.y.release(); S.z.release(); S.size.release(); S.bSlope.release(); S.bSize.release();
+    S.bRate.release(); S.bSum.release(); S.bPresc.release(); S.meta.release(); S.lidx.release();
+    S.culvertOf.release(); S.tab.release(); S.larea.release(); S.lflow.release();
+    S.H.release(); S.oldH.release(); S.Se.release(); S.K.release(); S.sink.release(); S.pond.release();
+    double **devOnly[] = {&S.bestH, &S.SeOld, &S.wFlow, &S.ldist, &S.mval, &S.b, &S.cap, &S.x0, &S.x1,
+                          &S.partA, &S.partB, &S.partC, &S.scratch};
+    for (double **p : devOnly) { dev_free(*p); *p = nullptr; }
+    dev_free(S.mcol); S.mcol = nullptr;
+    dev_free(S.ctrl); S.ctrl = nullptr;
+}
+
+double *scratch_buffer()
+{
+    if (!S.scratch) S.scratch = (double *)dev_alloc((size_t)S.N * sizeof(double));
+    return S.scratch;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- initializeSF3D (soilFluxes3D.cpp:49-178) ------------------------------------------------
+uint8_t sf3d_initialize(uint32_t nrNodes, uint32_t nrSurfaceNodes, uint8_t nrLateralLinks,
+                        int isComputeWater, int isComputeHeat, int isComputeSolutes, uint8_t hfMode)
+{
+    return guarded([&]() -> uint8_t {
+        uint8_t rc = sf3d_clean();
+        if (rc) return rc;
+        if (isComputeHeat)
+        {
+            fprintf(stderr, "[sf3d_b200] coupled heat is not built in this revision of the product\n");
+            return SF3D_PARAMETER_ERROR;
+        }
+        dev_select(g_device);
+        S.water = isComputeWater != 0; S.heat = isComputeHeat != 0; S.solutes = isComputeSolutes != 0;
+        S.heatVapor = S.heatAdvection = false; S.hfMode = 0;
+        if (S.heat) { S.heatVapor = true; S.heatAdvection = true; S.hfMode = hfMode; }
+        S.N = nrNodes; S.Ns = nrSurfaceNodes;
+        if (nrLateralLinks > SF3D_MAX_LATERAL_LINK) return SF3D_PARAMETER_ERROR;
+
+        const size_t N = nrNodes, L = (size_t)SF3D_NLINK * N;
+        S.x.alloc(N); S.y.alloc(N); S.z.alloc(N); S.size.alloc(N); S.meta.alloc(N); S.tab.alloc(N);
+        S.bSlope.alloc(N); S.bSize.alloc(N); S.bRate.alloc(N); S.bSum.alloc(N); S.bPresc.alloc(N);
+        S.lidx.alloc(L); S.larea.alloc(L); S.lflow.alloc(L);
+        S.H.alloc(N); S.oldH.alloc(N); S.Se.alloc(N); S.K.alloc(N); S.sink.alloc(N); S.pond.alloc(nrSurfaceNodes);
+        S.culvertOf.alloc(nrSurfaceNodes);
+        S.bestH = (double *)dev_alloc(N * 8); S.SeOld = (double *)dev_alloc(N * 8); S.wFlow = (double *)dev_alloc(N * 8);
+        S.ldist = (double *)dev_alloc(L * 8); S.mval = (double *)dev_alloc(L * 8); S.mcol = (uint32_t *)dev_alloc(L * 4);
+        S.b = (double *)dev_alloc(N * 8); S.cap = (double *)dev_alloc(N * 8);
+        S.x0 = (double *)dev_alloc(N * 8); S.x1 = (double *)dev_alloc(N * 8);
+        const size_t nb = (size_t)reduce_blocks(0xFFFFFFFFu);
+        S.partA = (double *)dev_alloc(nb * 8); S.partB = (double *)dev_alloc(nb * 8); S.partC = (double *)dev_alloc(nb * 8);
+        S.ctrl = (Ctrl *)dev_alloc(sizeof(Ctrl));
+
+        S.tablesDirty = S.topoDirty = true;
+        S.initialized = true;
+
+        // CPUSolver::initialize (cpusolver.cpp:25-31)
+        if (g_params.deltaTcurr == SF3D_NODATA) g_params.deltaTcurr = g_params.deltaTmax;
+        S.eng = Engine{};
+        S.eng.p = &g_params;
+        S.eng.computeWater = S.water;
+        fill_view();
+        return SF3D_OK;
+    }, (uint8_t)SF3D_MEMORY_ERROR);
+}
+
+// ---- initializeBalance (soilFluxes3D.cpp:184-197) ---------------------------------------------
+uint8_t sf3d_initialize_balance(void)
+{
+    return guarded([&]() -> uint8_t {
+        if (!S.initialized) return SF3D_MEMORY_ERROR;         // water.cpp:54-55
+        uint8_t rc = sync_to_device();
+        if (rc) return rc;
+        S.eng.initializeWaterBalance();
+        S.lflow.dev_written(); S.bSum.dev_written(); S.Se.dev_written();
+        if (!S.heat) S.eng.wholePeriod.heatMBR = 1.;          // soilFluxes3D.cpp:194
+        return SF3D_OK;
+    }, (uint8_t)SF3D_SOLVER_ERROR);
+}
+
+// ---- cleanSF3D (soilFluxes3D.cpp:218-304) -------------------------------------------------------
+uint8_t sf3d_clean(void)
+{
+    if (!S.initialized) return SF3D_OK;
+    release_all();
+    S.initialized = false;
+    S.soils.clear(); S.soilKeys.clear(); S.rough.clear();               // :295-296 (soil1DIndices and culvertList are not cleared)
+    S.tablesDirty = true;
+    return SF3D_OK;
+}
+
+uint8_t sf3d_initialize_heat_flag(uint8_t saveModeHeat, int adv, int lat)     // soilFluxes3D.cpp:325-332
+{
+    S.hfMode = saveModeHeat; S.heatAdvection = adv != 0; S.heatVapor = lat != 0;
+    return SF3D_OK;
+}
+
+uint32_t sf3d_set_threads_number(uint32_t nrThreads)                           // soilFluxes3D.cpp:340-361
+{
+    // Same clamping and return value as the reference; the product's parallelism is the GPU's.
+    uint32_t hw = std::thread::hardware_concurrency();
+    if (nrThreads < 1 || nrThreads > hw) nrThreads = hw;
+    return nrThreads;
+}
+void sf3d_set_use_lineal(int value) { g_useLineal = value != 0; }              // accepted, unused
+void sf3d_set_lineal_method(int value) { g_linealMethod = value; }
+
+
+// ---- setSoilProperties (soilFluxes3D.cpp:395-449) -------------------------------------------------
+uint8_t sf3d_set_soil_properties(uint16_t nrSoil, uint8_t nrHorizon, double VG_alpha, double VG_n, double VG_m,
+                                 double VG_he, double thetaR, double thetaS, double kSat, double MualemL,
+                                 double organicMatter, double clay)
+{
+    if (VG_alpha <= 0 || VG_n <= 1.0 || VG_m <= 0.0 || VG_m >= 1.0 || VG_he < 0.0 || kSat <= 0.0
+        || thetaR < 0.0 || thetaR >= 1.0 || thetaS <= 0.0 || thetaS > 1.0 || thetaR > thetaS)
+        return SF3D_PARAMETER_ERROR;
+    for (const auto &key : S.soilKeys)                                  // :410-412 already defined
+        if (key.first == nrSoil && key.second == nrHorizon) return SF3D_PARAMETER_ERROR;
+    if (S.soils.size() > 65535) return SF3D_MEMORY_ERROR;               // :415-418
+
+    SoilRec r{};
+    r.alpha = VG_alpha; r.n = VG_n; r.m = VG_m; r.he = VG_he;
+    r.Sc = pow(1. + pow(VG_alpha * VG_he, VG_n), -VG_m);                // :428
+    r.thetaR = thetaR; r.thetaS = thetaS; r.Ksat = kSat; r.L = MualemL;
+    r.organicMatter = organicMatter; r.clay = clay;
+    r.invM = 1.0 / r.m;
+    r.invSc = 1.0 / r.Sc;
+    r.ScPowInvM = pow(r.Sc, r.invM);
+    r.tDen = 1.0 - pow(1.0 - r.ScPowInvM, r.m);
+
+    if (nrSoil >= S.soil1D.size()) S.soil1D.resize((size_t)nrSoil + 1);
+    if (nrHorizon >= S.soil1D[nrSoil].size()) S.soil1D[nrSoil].resize((size_t)nrHorizon + 1);
+    S.soils.push_back(r);
+    S.soilKeys.emplace_back(nrSoil, nrHorizon);
+    S.soil1D[nrSoil][nrHorizon] = (uint16_t)(S.soils.size() - 1);
+    S.tablesDirty = true;
+    return SF3D_OK;
+}
+
+// ---- setSurfaceProperties (soilFluxes3D.cpp:457-467) --------------------------------------------------
+uint8_t sf3d_set_surface_properties(uint16_t surfaceIndex, double roughness)
+{
+    if (roughness < 0) return SF3D_PARAMETER_ERROR;
+    if (surfaceIndex >= S.rough.size()) S.rough.resize((size_t)surfaceIndex + 1);
+    S.rough[surfaceIndex] = roughness;
+    S.tablesDirty = true;
+    return SF3D_OK;
+}
+
+// ---- setNumericalParameters (soilFluxes3D.cpp:474-520) ------------------------------------------------
+uint8_t sf3d_set_numerical_parameters(double minDeltaT, double maxDeltaT, uint16_t maxIterationNumber,
+                                      uint16_t maxApproximationsNumber, uint8_t tolExp, uint8_t mbrExp)
+{
+    if (minDeltaT < 0.01) minDeltaT = 0.01;
+    if (minDeltaT > 3600.) minDeltaT = 3600.;
+    if (maxDeltaT < 60) maxDeltaT = 60;
+    if (maxDeltaT > 3600.) maxDeltaT = 3600.;
+    if (maxDeltaT < minDeltaT) maxDeltaT = minDeltaT;
+    if (maxIterationNumber < 20) maxIterationNumber = 20;
+    if (maxIterationNumber > 1000) maxIterationNumber = 1000;
+    if (maxApproximationsNumber < 1) maxApproximationsNumber = 1;
+    if (maxApproximationsNumber > 50) maxApproximationsNumber = 50;
+    if (tolExp < 5) tolExp = 5;
+    if (tolExp > 12) tolExp = 12;
+    if (mbrExp < 1) mbrExp = 1;
+    if (mbrExp > 9) mbrExp = 9;
+    g_params.MBRThreshold = pow(10.0, -mbrExp);
+    g_params.residualTolerance = pow(10.0, -tolExp);
+    g_params.deltaTmin = minDeltaT;
+    g_params.deltaTmax = maxDeltaT;
+    // deltaTcurr is passed through unchanged (:514)
+    g_params.maxApproximationsNumber = maxApproximationsNumber;
+    g_params.maxIterationsNumber = maxIterationNumber;
+    return SF3D_OK;
+}
+
+// ---- setHydraulicProperties (soilFluxes3D.cpp:531-548) ------------------------------------------------
+uint8_t sf3d_set_hydraulic_properties(uint8_t wrc, uint8_t meanType, float ratio)
+{
+    if ((ratio < 0.1) || (ratio > 100)) return SF3D_PARAMETER_ERROR;
+    g_params.wrcModel = wrc;
+    g_params.meanType = meanType;
+    g_params.lateralVerticalRatio = ratio;       // float -> double, as SolverParametersPartial does
+    return SF3D_OK;
+}
+
+// ---- setNodeBoundary (soilFluxes3D.cpp:689-725) ---------------------------------------------------------
+static uint8_t set_node_boundary_unchecked(uint32_t i, uint8_t bt, double slope, double bArea)
+{
+    uint32_t *meta = S.meta.rw();
+    meta[i] = (meta[i] & ~0xFu) | (bt & 0xFu);
+    if (bt == BT_NONE) return SF3D_OK;
+    S.bSlope.rw()[i] = slope;
+    S.bSize.rw()[i] = bArea;
+    if (S.water)
+    {
+        S.bRate.rw()[i] = 0.;
+        S.bSum.rw()[i] = 0.;
+        S.bPresc.rw()[i] = SF3D_NODATA;
+    }
+    return SF3D_OK;
+}
+uint8_t sf3d_set_node_boundary(uint32_t nodeIndex, uint8_t boundaryType, double slope, double boundaryArea)
+{
+    return guarded([&]() -> uint8_t {
+        REQUIRE_INIT_E(); REQUIRE_INDEX_E(nodeIndex);       // (the reference has no checks here)
+        return set_node_boundary_unchecked(nodeIndex, boundaryType, slope, boundaryArea);
+    }, (uint8_t)SF3D_MEMORY_ERROR);
+}
+
+// ---- setCulvert (soilFluxes3D.cpp:551-588) ---------------------------------------------------------------
+uint8_t sf3d_set_culvert(uint32_t nodeIndex, double roughness, double slope, double width, double height)
+{
+    return guarded([&]() -> uint8_t {
+        REQUIRE_INIT_E();
+        if (nodeIndex >= S.N || !is_surface(nodeIndex) || nodeIndex >= S.Ns) return SF3D_INDEX_ERROR;
+        set_node_boundary_unchecked(nodeIndex, BT_CULVERT, slope, width * height);
+        size_t k = 0;
+        for (; k < S.culverts.size(); ++k)
+            if (S.culverts[k].roughness == roughness && S.culverts[k].width == width && S.culverts[k].height == height) break;
+        if (k == S.culverts.size()) { S.culverts.push_back(CulvertRec{width, height, roughness}); S.tablesDirty = true; }
+        S.culvertOf.rw()[nodeIndex] = (uint32_t)k;
+        return SF3D_OK;
+    }, (uint8_t)SF3D_MEMORY_ERROR);
+}
+
+// ---- setNode (soilFluxes3D.cpp:595-629) ---------------------------------------------------------------------
+uint8_t sf3d_set_node(uint32_t index, double x, double y, double z, double volume_or_area, int isSurface,
+                      uint8_t boundaryType, double slope, double boundaryArea)
+{
+    return guarded([&]() -> uint8_t {
+        REQUIRE_INIT_E(); REQUIRE_INDEX_E(index);
+        S.x.rw()[index] = x; S.y.rw()[index] = y; S.z.rw()[index] = z; S.size.rw()[index] = volume_or_area;
+        uint32_t *meta = S.meta.rw();
+        meta[index] = (meta[index] & ~(1u << 4)) | ((isSurface ? 1u : 0u) << 4);
+        set_node_boundary_unchecked(index, boundaryType, slope, boundaryArea);
+        if (S.water)
+        {
+            if (isSurface && index < S.Ns) S.pond.rw()[index] = (double)0.0001f;     // :616 (float literal)
+            S.sink.rw()[index] = 0.;
+        }
+        S.topoDirty = true;
+        return SF3D_OK;
+    }, (uint8_t)SF3D_MEMORY_ERROR);
+}
+
+// ---- setNodeLink (soilFluxes3D.cpp:636-683) -------------------------------------------------------------------
+uint8_t sf3d_set_node_link(uint32_t nodeIndex, uint32_t linkIndex, uint8_t direction, double interfaceArea)
+{
+    return guarded([&]() -> uint8_t {
+        REQUIRE_INIT_E();
+        if (nodeIndex >= S.N || linkIndex >= S.N) return SF3D_INDEX_ERROR;
+        uint32_t *meta = S.meta.rw();
+        uint32_t m = meta[nodeIndex];
+        uint32_t slot;
+        switch (direction)
+        {
+            case 1: slot = 0; break;                 // Up
+            case 2: slot = 1; break;                 // Down
+            case 3:                                  // Lateral
+            {
+                const uint32_t nLat = META_NLAT(m);
+                if (nLat == SF3D_MAX_LATERAL_LINK) return SF3D_TOPOGRAPHY_ERROR;
+                slot = 2 + nLat;
+                m = (m & ~(0xFu << 5)) | ((nLat + 1) << 5);
+                break;
+            }
+            default: return SF3D_PARAMETER_ERROR;
+        }
+        m |= (1u << (9 + slot));
+        meta[nodeIndex] = m;
+        const size_t li = (size_t)slot * S.N + nodeIndex;
+        S.lidx.rw()[li] = linkIndex;
+        S.larea.rw()[li] = interfaceArea;
+        if (S.water) S.lflow.rw()[li] = 0.;
+        S.topoDirty = true;
+        return SF3D_OK;
+    }, (uint8_t)SF3D_MEMORY_ERROR);
+}
+
+// ---- setNodeSoil / setNodeSurface (soilFluxes3D.cpp:734-775) ------------------------------------------------------
+uint8_t sf3d_set_node_soil(uint32_t nodeIndex, uint16_t soilIndex, uint16_t horizonIndex)
+{
+    return guarded([&]() -> uint8_t {
+        REQUIRE_INIT_E(); REQUIRE_INDEX_E(nodeIndex);
+        if (is_surface(nodeIndex)) return SF3D_INDEX_ERROR;
+        if (soilIndex >= S.soil1D.size() || horizonIndex >= S.soil1D[soilIndex].size()) return SF3D_PARAMETER_ERROR;
+        S.tab.rw()[nodeIndex] = S.soil1D[soilIndex][horizonIndex];
+        return SF3D_OK;
+    }, (uint8_t)SF3D_MEMORY_ERROR);
+}
+uint8_t sf3d_set_node_surface(uint32_t nodeIndex, uint16_t surfaceIndex)
+{
+    return guarded([&]() -> uint8_t {
+        REQUIRE_INIT_E(); REQUIRE_INDEX_E(nodeIndex);
+        if (surfaceIndex >= S.rough.size()) return SF3D_PARAMETER_ERROR;
+        if (!is_surface(nodeIndex)) return SF3D_INDEX_ERROR;
+        S.tab.rw()[nodeIndex] = surfaceIndex;
+        return SF3D_OK;
+    }, (uint8_t)SF3D_MEMORY_ERROR);
+}
+
+// ---- water setters (soilFluxes3D.cpp:783-945) -----------------------------------------------------------------------
+uint8_t sf3d_set_node_pond(uint32_t nodeIndex, double pond)
+{
+    return guarded([&]() -> uint8_t {
+        REQUIRE_INIT_E(); REQUIRE_INDEX_E(nodeIndex);
+        if (!is_surface(nodeIndex) || nodeIndex >= S.Ns) return SF3D_INDEX_ERROR;
+        S.pond.rw()[nodeIndex] = pond;
+        return SF3D_OK;
+    }, (uint8_t)SF3D_MEMORY_ERROR);
+}
+
+static void set_head_and_state(uint32_t i, double H, bool fromSe, double Se)
+{
+    S.H.rw()[i] = H;
+    S.oldH.rw()[i] = H;
+    if (is_surface(i)) return;
+    if (!fromSe) Se = sf3d_node_se(node_soil(i), g_params.wrcModel, H, S.z.ro()[i]);
+    S.Se.rw()[i] = Se;
+    S.K.rw()[i] = host_node_K(i, Se);
+}
+
+uint8_t sf3d_set_node_water_content(uint32_t nodeIndex, double waterContent)
+{
+    return guarded([&]() -> uint8_t {
+        REQUIRE_INIT_E(); REQUIRE_INDEX_E(nodeIndex);
+        if (waterContent < 0.) return SF3D_PARAMETER_ERROR;
+        if (is_surface(nodeIndex))
+        {
+            const double H = S.z.ro()[nodeIndex] + waterContent;
+            S.H.rw()[nodeIndex] = H; S.oldH.rw()[nodeIndex] = H;
+            S.Se.rw()[nodeIndex] = 1.; S.K.rw()[nodeIndex] = 0.;
+        }
+        else
+        {
+            if (waterContent > 1.) return SF3D_PARAMETER_ERROR;
+            const SoilRec &s = node_soil(nodeIndex);
+            const double Se = host_se_from_theta(s, waterContent);
+            set_head_and_state(nodeIndex, S.z.ro()[nodeIndex] - host_psi_from_se(s, Se), true, Se);
+        }
+        return SF3D_OK;
+    }, (uint8_t)SF3D_MEMORY_ERROR);
+}
+uint8_t sf3d_set_node_degree_of_saturation(uint32_t nodeIndex, double Se)
+{
+    return guarded([&]() -> uint8_t {
+        REQUIRE_INIT_E(); REQUIRE_INDEX_E(nodeIndex);
+        if (is_surface(nodeIndex)) return SF3D_INDEX_ERROR;
+        if (Se < 0. || Se > 1.) return SF3D_PARAMETER_ERROR;
+        set_head_and_state(nodeIndex, S.z.ro()[nodeIndex] - host_psi_from_se(node_soil(nodeIndex), Se), true, Se);
+        return SF3D_OK;
+    }, (uint8_t)SF3D_MEMORY_ERROR);
+}
+static uint8_t set_potential(uint32_t i, double H)
+{
+    S.H.rw()[i] = H; S.oldH.rw()[i] = H;
+    if (is_surface(i)) { S.Se.rw()[i] = 1.; S.K.rw()[i] = SF3D_NODATA; }
+    else set_head_and_state(i, H, false, 0.);
+    return SF3D_OK;
+}
+uint8_t sf3d_set_node_matric_potential(uint32_t nodeIndex, double psi)
+{
+    return guarded([&]() -> uint8_t {
+        REQUIRE_INIT_E(); REQUIRE_INDEX_E(nodeIndex);
+        return set_potential(nodeIndex, S.z.ro()[nodeIndex] + psi);
+    }, (uint8_t)SF3D_MEMORY_ERROR);
+}
+uint8_t sf3d_set_node_total_potential(uint32_t nodeIndex, double H)
+{
+    return guarded([&]() -> uint8_t {
+        REQUIRE_INIT_E(); REQUIRE_INDEX_E(nodeIndex);
+        return set_potential(nodeIndex, H);
+    }, (uint8_t)SF3D_MEMORY_ERROR);
+}
+uint8_t sf3d_set_node_water_sink_source(uint32_t nodeIndex, double q)
+{
+    return guarded([&]() -> uint8_t {
+        REQUIRE_INIT_E(); REQUIRE_INDEX_E(nodeIndex);
+        S.sink.rw()[nodeIndex] = q;
+        return SF3D_OK;
+    }, (uint8_t)SF3D_MEMORY_ERROR);
+}
+uint8_t sf3d_set_node_prescribed_total_potential(uint32_t nodeIndex, double H)
+{
+    return guarded([&]() -> uint8_t {
+        REQUIRE_INIT_E(); REQUIRE_INDEX_E(nodeIndex);
+        if (node_bt(nodeIndex) != BT_PRESCRIBED) return SF3D_BOUNDARY_ERROR;
+        S.bPresc.rw()[nodeIndex] = H;
+        return SF3D_OK;
+    }, (uint8_t)SF3D_MEMORY_ERROR);
+}
+
+// ---- water getters (soilFluxes3D.cpp:951-1277) ---------------------------------------------------------------------------
+#define GETTER_PROLOGUE(i) REQUIRE_INIT_D(); REQUIRE_INDEX_D(i)
+#define GUARDED_D(...) return guarded([&]() -> double { __VA_ARGS__ }, err_value(SF3D_MEMORY_ERROR))
+
+double sf3d_get_node_water_content(uint32_t i)
+{ GUARDED_D( GETTER_PROLOGUE(i);
+    return is_surface(i) ? (S.H.ro()[i] - S.z.ro()[i]) : sf3d_theta_from_se(node_soil(i), S.Se.ro()[i]); ); }
+double sf3d_get_node_maximum_water_content(uint32_t i)
+{ GUARDED_D( GETTER_PROLOGUE(i); if (is_surface(i)) return err_value(SF3D_INDEX_ERROR); return node_soil(i).thetaS; ); }
+double sf3d_get_node_minimum_water_content(uint32_t i)
+{ GUARDED_D( GETTER_PROLOGUE(i); if (is_surface(i)) return err_value(SF3D_INDEX_ERROR); return node_soil(i).thetaR; ); }
+double sf3d_get_node_available_water_content(uint32_t i)
+{ GUARDED_D( GETTER_PROLOGUE(i);
+    if (is_surface(i)) return S.H.ro()[i] - S.z.ro()[i];
+    const SoilRec &s = node_soil(i);
+    return sf3d_max(0., sf3d_theta_from_se(s, S.Se.ro()[i]) - sf3d_theta_from_signed_psi(s, g_params.wrcModel, -160)); ); }
+double sf3d_get_node_water_deficit(uint32_t i, double fieldCapacity)
+{ GUARDED_D( GETTER_PROLOGUE(i);
+    if (is_surface(i)) return 0.;
+    const SoilRec &s = node_soil(i);
+    return sf3d_theta_from_signed_psi(s, g_params.wrcModel, -fieldCapacity) - sf3d_theta_from_se(s, S.Se.ro()[i]); ); }
+double sf3d_get_node_degree_of_saturation(uint32_t i)
+{ GUARDED_D( GETTER_PROLOGUE(i);
+    if (!is_surface(i)) return S.Se.ro()[i];
+    const double curPot = S.H.ro()[i] - S.z.ro()[i], maxPot = 0.001;
+    return curPot <= 0 ? 0 : (curPot > maxPot ? 1. : curPot / maxPot); ); }
+double sf3d_get_node_water_conductivity(uint32_t i) { GUARDED_D( GETTER_PROLOGUE(i); return S.K.ro()[i]; ); }
+double sf3d_get_node_matric_potential(uint32_t i) { GUARDED_D( GETTER_PROLOGUE(i); return S.H.ro()[i] - S.z.ro()[i]; ); }
+double sf3d_get_node_total_potential(uint32_t i) { GUARDED_D( GETTER_PROLOGUE(i); return S.H.ro()[i]; ); }
+double sf3d_get_node_pond(uint32_t i)
+{ GUARDED_D( GETTER_PROLOGUE(i); if (!is_surface(i) || i >= S.Ns) return err_value(SF3D_INDEX_ERROR); return S.pond.ro()[i]; ); }
+
+double sf3d_get_node_max_water_flow(uint32_t i, uint8_t direction)
+{ GUARDED_D( GETTER_PROLOGUE(i);
+    const double *lf = S.lflow.ro();
+    const uint32_t m = S.meta.ro()[i];
+    switch (direction)
+    {
+        case 1: return lf[i];                       // linkIndex is calloc'ed, never noDataU: always the stored sum
+        case 2: return lf[(size_t)S.N + i];
+        case 3:
+        {
+            double mx = 0.;
+            for (uint32_t l = 0; l < META_NLAT(m); ++l) mx = sf3d_max(mx, lf[(size_t)(2 + l) * S.N + i]);
+            return mx;
+        }
+        default: return err_value(SF3D_INDEX_ERROR);
+    } ); }
+static double lateral_sum(uint32_t i, int sign)
+{
+    const double *lf = S.lflow.ro();
+    const uint32_t m = S.meta.ro()[i];
+    double sum = 0.;
+    for (uint32_t l = 0; l < META_NLAT(m); ++l)
+    {
+        const double f = lf[(size_t)(2 + l) * S.N + i];
+        if (sign == 0 || (sign > 0 && f > 0) || (sign < 0 && f < 0)) sum += f;
+    }
+    return sum;
+}
+double sf3d_get_node_sum_lateral_water_flow(uint32_t i) { GUARDED_D( GETTER_PROLOGUE(i); return lateral_sum(i, 0); ); }
+double sf3d_get_node_sum_lateral_water_flow_in(uint32_t i) { GUARDED_D( GETTER_PROLOGUE(i); return lateral_sum(i, 1); ); }
+double sf3d_get_node_sum_lateral_water_flow_out(uint32_t i) { GUARDED_D( GETTER_PROLOGUE(i); return lateral_sum(i, -1); ); }
+double sf3d_get_node_boundary_water_flow(uint32_t i)
+{ GUARDED_D( GETTER_PROLOGUE(i); if (node_bt(i) == BT_NONE) return err_value(SF3D_BOUNDARY_ERROR); return S.bSum.ro()[i]; ); }
+
+double sf3d_get_total_boundary_water_flow(uint8_t boundaryType)
+{ GUARDED_D(
+    if (!S.initialized) return 0.;
+    if (sync_to_device()) return 0.;
+    return S.eng.totalBoundaryWaterFlow(boundaryType); ); }
+double sf3d_get_total_water_content(void)
+{ GUARDED_D(
+    if (!S.initialized) return -1;                  // water.cpp:73-74
+    if (sync_to_device()) return -1;
+    return S.eng.totalWaterContent(); ); }
+double sf3d_get_water_storage(void) { return S.eng.curStep.waterStorage; }
+double sf3d_get_water_mbr(void) { return S.eng.wholePeriod.waterMBR; }
+
+// ---- heat API (soilFluxes3D.cpp:1283-1753): heat milestone ------------------------------------------------------------------
+#define HEAT_SETTER(name) uint8_t name(uint32_t i, double) { REQUIRE_INIT_E(); REQUIRE_INDEX_E(i); return SF3D_MISSING_DATA_ERROR; }
+HEAT_SETTER(sf3d_set_node_heat_sink_source)
+HEAT_SETTER(sf3d_set_node_temperature)
+HEAT_SETTER(sf3d_set_node_boundary_height_wind)
+HEAT_SETTER(sf3d_set_node_boundary_height_temperature)
+HEAT_SETTER(sf3d_set_node_boundary_net_irradiance)
+HEAT_SETTER(sf3d_set_node_boundary_temperature)
+HEAT_SETTER(sf3d_set_node_boundary_relative_humidity)
+HEAT_SETTER(sf3d_set_node_boundary_roughness)
+HEAT_SETTER(sf3d_set_node_boundary_wind_speed)
+uint8_t sf3d_set_node_boundary_fixed_temperature(uint32_t i, double, double) { REQUIRE_INIT_E(); REQUIRE_INDEX_E(i); return SF3D_MISSING_DATA_ERROR; }
+#define HEAT_GETTER(name, code) double name(uint32_t i) { REQUIRE_INIT_D(); REQUIRE_INDEX_D(i); return err_value(code); }
+HEAT_GETTER(sf3d_get_node_temperature, SF3D_TOPOGRAPHY_ERROR)           // !isHeatNode -> TopographyError (:1494)
+HEAT_GETTER(sf3d_get_node_heat_conductivity, SF3D_TOPOGRAPHY_ERROR)
+HEAT_GETTER(sf3d_get_node_vapor, SF3D_MISSING_DATA_ERROR)
+HEAT_GETTER(sf3d_get_node_boundary_advective_flux, SF3D_MISSING_DATA_ERROR)
+HEAT_GETTER(sf3d_get_node_boundary_latent_flux, SF3D_MISSING_DATA_ERROR)
+HEAT_GETTER(sf3d_get_node_boundary_radiative_flux, SF3D_MISSING_DATA_ERROR)
+HEAT_GETTER(sf3d_get_node_boundary_sensible_flux, SF3D_MISSING_DATA_ERROR)
+HEAT_GETTER(sf3d_get_node_boundary_aerodynamic_conductance, SF3D_MISSING_DATA_ERROR)
+HEAT_GETTER(sf3d_get_node_boundary_soil_conductance, SF3D_MISSING_DATA_ERROR)
+double sf3d_get_node_heat_storage(uint32_t i, double) { REQUIRE_INIT_D(); REQUIRE_INDEX_D(i); return err_value(SF3D_MISSING_DATA_ERROR); }
+double sf3d_get_node_heat_max_flux(uint32_t i, uint8_t, uint8_t) { REQUIRE_INIT_D(); REQUIRE_INDEX_D(i); return err_value(SF3D_TOPOGRAPHY_ERROR); }
+double sf3d_get_heat_mbr(void) { return S.eng.wholePeriod.heatMBR; }
+double sf3d_get_heat_mbe(void) { return S.eng.wholePeriod.heatMBE; }
+
+// ---- computation (soilFluxes3D.cpp:1760-1821) ----------------------------------------------------------------------------------
+double sf3d_compute_step(double maxTimeStep)
+{
+    return guarded([&]() -> double {
+        if (!S.initialized) return err_value(SF3D_MEMORY_ERROR);
+        if (sync_to_device()) return err_value(SF3D_TOPOGRAPHY_ERROR);
+        const double dt = S.eng.computeStep(maxTimeStep);
+        step_wrote_device();
+        return dt;
+    }, err_value(SF3D_MEMORY_ERROR));
+}
+void sf3d_compute_period(double timePeriod)
+{
+    guarded([&]() -> int {
+        if (!S.initialized) return 0;
+        if (sync_to_device()) return 0;
+        S.eng.computePeriod(timePeriod);
+        step_wrote_device();
+        return 0;
+    }, 0);
+}
+
+// ====================================== extensions ===================================================
+uint8_t sf3d_ext_get_field(int field, uint32_t first, uint32_t count, double *dst)
+{
+    return guarded([&]() -> uint8_t {
+        REQUIRE_INIT_E();
+        if (!dst) return SF3D_PARAMETER_ERROR;
+        if ((uint64_t)first + count > S.N) return SF3D_INDEX_ERROR;
+        switch (field)
+        {
+            case SF3D_F_WATER_CONTENT: case SF3D_F_DEGREE_OF_SATURATION: case SF3D_F_WATER_CONDUCTIVITY:
+            case SF3D_F_MATRIC_POTENTIAL: case SF3D_F_TOTAL_POTENTIAL: case SF3D_F_POND:
+            case SF3D_F_BOUNDARY_WATER_FLOW: case SF3D_F_SUM_LATERAL_FLOW: case SF3D_F_MAX_FLOW_UP:
+            case SF3D_F_MAX_FLOW_DOWN: case SF3D_F_MAX_FLOW_LATERAL: case SF3D_F_TEMPERATURE:
+                break;
+            default: return SF3D_PARAMETER_ERROR;
+        }
+        uint8_t rc = sync_to_device();
+        if (rc) return rc;
+        if (field == SF3D_F_TOTAL_POTENTIAL)        // getNodeTotalPotential is the array itself: one copy
+        {
+            d2h(dst, S.H.d + first, (size_t)count * sizeof(double));
+            return SF3D_OK;
+        }
+        double *tmp = scratch_buffer();
+        k_get_field(S.eng.v, field, first, count, tmp);
+        d2h(dst, tmp, (size_t)count * sizeof(double));
+        return SF3D_OK;
+    }, (uint8_t)SF3D_MEMORY_ERROR);
+}
+
+uint8_t sf3d_ext_set_field(int field, uint32_t first, uint32_t count, const double *src)
+{
+    return guarded([&]() -> uint8_t {
+        REQUIRE_INIT_E();
+        if (!src) return SF3D_PARAMETER_ERROR;
+        if ((uint64_t)first + count > S.N) return SF3D_INDEX_ERROR;
+        switch (field)
+        {
+            case SF3D_F_WATER_SINK_SOURCE:          // setNodeWaterSinkSource over a range: one copy
+                S.sink.push();
+                h2d(S.sink.d + first, src, (size_t)count * sizeof(double));
+                S.sink.dev_written();
+                return SF3D_OK;
+            case SF3D_F_MATRIC_POTENTIAL: case SF3D_F_TOTAL_POTENTIAL:
+            {
+                uint8_t rc = sync_to_device();
+                if (rc) return rc;
+                double *tmp = scratch_buffer();
+                h2d(tmp, src, (size_t)count * sizeof(double));
+                k_set_potential(S.eng.v, first, count, tmp, field == SF3D_F_TOTAL_POTENTIAL);
+                S.H.dev_written(); S.oldH.dev_written(); S.Se.dev_written(); S.K.dev_written();
+                return SF3D_OK;
+            }
+            default: break;
+        }
+        // remaining fields: the scalar setter per node on the host mirrors
+        uint8_t firstErr = SF3D_OK;
+        for (uint32_t k = 0; k < count; ++k)
+        {
+            const uint32_t i = first + k;
+            uint8_t rc;
+            switch (field)
+            {
+                case SF3D_F_WATER_CONTENT:        rc = sf3d_set_node_water_content(i, src[k]); break;
+                case SF3D_F_DEGREE_OF_SATURATION: rc = sf3d_set_node_degree_of_saturation(i, src[k]); break;
+                case SF3D_F_POND:                 rc = sf3d_set_node_pond(i, src[k]); break;
+                case SF3D_F_PRESCRIBED_POTENTIAL: rc = sf3d_set_node_prescribed_total_potential(i, src[k]); break;
+                case SF3D_F_TEMPERATURE:          rc = sf3d_set_node_temperature(i, src[k]); break;
+                case SF3D_F_HEAT_SINK_SOURCE:     rc = sf3d_set_node_heat_sink_source(i, src[k]); break;
+                case SF3D_F_BOUNDARY_NET_IRRADIANCE:    rc = sf3d_set_node_boundary_net_irradiance(i, src[k]); break;
+                case SF3D_F_BOUNDARY_TEMPERATURE:       rc = sf3d_set_node_boundary_temperature(i, src[k]); break;
+                case SF3D_F_BOUNDARY_RELATIVE_HUMIDITY: rc = sf3d_set_node_boundary_relative_humidity(i, src[k]); break;
+                case SF3D_F_BOUNDARY_WIND_SPEED:        rc = sf3d_set_node_boundary_wind_speed(i, src[k]); break;
+                default: return SF3D_PARAMETER_ERROR;
+            }
+            if (rc && !firstErr) firstErr = rc;
+        }
+        return firstErr;
+    }, (uint8_t)SF3D_MEMORY_ERROR);
+}
+
+uint8_t sf3d_ext_get_link_table(uint8_t slot, uint32_t first, uint32_t count, uint8_t *lt, uint32_t *li, double *area)
+{
+    return guarded([&]() -> uint8_t {
+        REQUIRE_INIT_E();
+        if (slot >= SF3D_NLINK || (uint64_t)first + count > S.N) return SF3D_INDEX_ERROR;
+        const uint32_t *meta = S.meta.ro();
+        const uint32_t *lidx = S.lidx.ro();
+        const double *larea = S.larea.ro();
+        for (uint32_t k = 0; k < count; ++k)
+        {
+            const uint32_t i = first + k;
+            const bool has = META_HAS_SLOT(meta[i], slot);
+            if (lt) lt[k] = has ? (slot == 0 ? 1 : (slot == 1 ? 2 : 3)) : 0;
+            if (li) li[k] = has ? lidx[(size_t)slot * S.N + i] : 0u;
+            if (area) area[k] = has ? larea[(size_t)slot * S.N + i] : 0.;
+        }
+        return SF3D_OK;
+    }, (uint8_t)SF3D_MEMORY_ERROR);
+}
+
+uint8_t sf3d_ext_get_node_meta(uint32_t first, uint32_t count, uint8_t *sfl, uint8_t *bt, uint8_t *nl)
+{
+    return guarded([&]() -> uint8_t {
+        REQUIRE_INIT_E();
+        if ((uint64_t)first + count > S.N) return SF3D_INDEX_ERROR;
+        const uint32_t *meta = S.meta.ro();
+        for (uint32_t k = 0; k < count; ++k)
+        {
+            const uint32_t m = meta[first + k];
+            if (sfl) sfl[k] = (uint8_t)META_SURFACE(m);
+            if (bt) bt[k] = (uint8_t)META_BT(m);
+            if (nl) nl[k] = (uint8_t)META_NLAT(m);
+        }
+        return SF3D_OK;
+    }, (uint8_t)SF3D_MEMORY_ERROR);
+}
+
+uint8_t sf3d_ext_build_grid(const sf3d_grid_desc *g)
+{
+    return guarded([&]() -> uint8_t {
+        REQUIRE_INIT_E();
+        if (!g || !g->dem || !g->cell_rank || !g->layer_depth || !g->layer_thickness) return SF3D_PARAMETER_ERROR;
+        const uint64_t cells = (uint64_t)g->rows * g->cols;
+        if ((uint64_t)g->layers * g->n_valid != S.N || g->n_valid != S.Ns) return SF3D_INDEX_ERROR;
+
+        // soil-table row of every (soil id, layer) pair; setNodeSoil's checks (soilFluxes3D.cpp:745-746)
+        uint32_t nSoilIds = 1;
+        if (g->soil_id) for (uint64_t c = 0; c < cells; ++c) if (g->cell_rank[c] >= 0) nSoilIds = std::max<uint32_t>(nSoilIds, g->soil_id[c] + 1u);
+        std::vector<uint16_t> layerTab((size_t)g->layers * nSoilIds, 0);
+        std::vector<uint8_t> used(nSoilIds, g->soil_id ? 0 : 1);
+        if (g->soil_id) for (uint64_t c = 0; c < cells; ++c) if (g->cell_rank[c] >= 0) used[g->soil_id[c]] = 1;
+        for (uint32_t l = 1; l < g->layers; ++l)
+            for (uint32_t sid = 0; sid < nSoilIds; ++sid)
+            {
+                if (!used[sid]) continue;
+                const uint16_t hz = g->layer_horizon ? g->layer_horizon[l] : 0;
+                if (sid >= S.soil1D.size() || hz >= S.soil1D[sid].size()) return SF3D_PARAMETER_ERROR;
+                layerTab[(size_t)l * nSoilIds + sid] = S.soil1D[sid][hz];
+            }
+        if (g->surface_id) for (uint64_t c = 0; c < cells; ++c)
+            if (g->cell_rank[c] >= 0 && g->surface_id[c] >= S.rough.size()) return SF3D_PARAMETER_ERROR;
+
+        uint8_t rc = sync_to_device(false);     // pushes anything set so far; view is current
+        if (rc) return rc;
+
+        std::vector<void *> tmp;
+        auto up = [&](const void *src, size_t bytes) -> void * {
+            if (!src) return nullptr;
+            void *d = dev_alloc(bytes); h2d(d, src, bytes); tmp.push_back(d); return d;
+        };
+        GridDev gd{};
+        gd.rows = g->rows; gd.cols = g->cols; gd.layers = g->layers; gd.nValid = g->n_valid;
+        gd.cell = g->cell; gd.xll = g->x_ll; gd.yll = g->y_ll;
+        gd.dem = (const float *)up(g->dem, cells * 4);
+        gd.slope = (const float *)up(g->slope_tan, cells * 4);
+        gd.rank = (const int32_t *)up(g->cell_rank, cells * 4);
+        gd.outlet = (const uint8_t *)up(g->outlet, cells);
+        gd.boundaryL1 = (const uint8_t *)up(g->boundary_l1, cells);
+        gd.soilId = (const uint16_t *)up(g->soil_id, cells * 2);
+        gd.surfaceId = (const uint16_t *)up(g->surface_id, cells * 2);
+        gd.pond = (const double *)up(g->pond, cells * 8);
+        gd.layerDepth = (const double *)up(g->layer_depth, (size_t)g->layers * 8);
+        gd.layerThickness = (const double *)up(g->layer_thickness, (size_t)g->layers * 8);
+        gd.layerTab = (const uint16_t *)up(layerTab.data(), layerTab.size() * 2);
+        gd.nSoilIds = nSoilIds;
+        gd.freeRunoff = g->free_catchment_runoff; gd.freeLateral = g->free_lateral_drainage; gd.freeBottom = g->free_bottom_drainage;
+        gd.computeWater = S.water; gd.computeHeat = S.heat;
+        k_build_grid(S.eng.v, gd);
+        dev_sync();
+        for (void *d : tmp) dev_free(d);
+
+        S.x.dev_written(); S.y.dev_written(); S.z.dev_written(); S.size.dev_written(); S.meta.dev_written();
+        S.tab.dev_written(); S.bSlope.dev_written(); S.bSize.dev_written(); S.bRate.dev_written();
+        S.bSum.dev_written(); S.bPresc.dev_written(); S.lidx.dev_written(); S.larea.dev_written();
+        S.sink.dev_written(); S.pond.dev_written();
+        S.topoDirty = true;
+        return SF3D_OK;
+    }, (uint8_t)SF3D_MEMORY_ERROR);
+}
+
+uint8_t sf3d_ext_get_counters(sf3d_counters *out)
+{
+    if (!out) return SF3D_PARAMETER_ERROR;
+    sf3d_counters c = S.eng.cnt;
+    c.kernel_launches = launches();
+    c.delta_t_curr = g_params.deltaTcurr;
+    c.last_courant = S.eng.courantWater;
+    c.last_mbr = S.eng.curStep.waterMBR;
+    c.last_mbe = S.eng.curStep.waterMBE;
+    c.links = 0;
+    if (S.initialized)
+        c.links = guarded([&]() -> uint64_t { if (sync_to_device(false)) return 0; return k_count_links(S.eng.v); }, (uint64_t)0);
+    *out = c;
+    return SF3D_OK;
+}
+uint8_t sf3d_ext_reset_counters(void) { memset(&S.eng.cnt, 0, sizeof S.eng.cnt); return SF3D_OK; }
+const char *sf3d_ext_backend(void) { return "b200"; }
+uint8_t sf3d_ext_set_device(int device)
+{
+    if (S.initialized) return SF3D_PARAMETER_ERROR;     // choose the device before initializeSF3D
+    g_device = device;
+    return SF3D_OK;
+}
+
+uint8_t sf3d_ext_reset_solver(void) { g_params = default_params(); return SF3D_OK; }
+void *sf3d_ext_stream(void) { return guarded([&]() -> void * { return dev_stream(); }, (void *)nullptr); }
+uint8_t sf3d_ext_profile(int enable)
+{ return guarded([&]() -> uint8_t { prof_enable(enable != 0); return SF3D_OK; }, (uint8_t)SF3D_SOLVER_ERROR); }
+uint8_t sf3d_ext_get_kernel_times(sf3d_kernel_times *out)
+{
+    if (!out) return SF3D_PARAMETER_ERROR;
+    return guarded([&]() -> uint8_t { prof_get(out->ms, out->launches); return SF3D_OK; }, (uint8_t)SF3D_SOLVER_ERROR);
+}
+
+}  // extern "C"

@@ -1,0 +1,298 @@
+// sf3d_engine.cpp -- host control loop of the water time step (see sf3d_engine.h).
+// The decision tree is the reference's; the per-node work is launched as kernels and only the
+// reduced scalars (Courant max, residual status, storage, sink sum) are read back: two to three
+// stream synchronisations per Picard approximation.
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+#include "sf3d_engine.h"
+
+namespace sf3d {
+
+SolverParams default_params()
+{
+    SolverParams p{};
+    p.MBRThreshold = 1e-3;
+    p.residualTolerance = 1e-10;
+    p.deltaTmin = 1.;
+    p.deltaTmax = 600.;
+    p.deltaTcurr = SF3D_NODATA;
+    p.maxApproximationsNumber = 10;
+    p.maxIterationsNumber = 200;
+    p.wrcModel = 1;                 // ModifiedVanGenuchten
+    p.meanType = 2;                 // Logarithmic
+    p.lateralVerticalRatio = 4.;
+    p.heatWeightFactor = 0.5;
+    p.CourantWaterThreshold = 0.5;
+    p.instabilityFactor = 10.;
+    return p;
+}
+
+// Solver::calcCurrentMaxIterationNumber (solver.h:55-59): float arithmetic, then max(.., 25)
+uint32_t Engine::calcCurrentMaxIterationNumber(int approx) const
+{
+    uint32_t n = static_cast<uint32_t>((approx + 1) * (static_cast<float>(p->maxIterationsNumber)
+                                                       / static_cast<float>(p->maxApproximationsNumber)));
+    return std::max(n, 25u);
+}
+
+// soilFluxes3D.cpp:1785-1821 (heat continuation: heat milestone)
+double Engine::computeStep(double maxTimeStep)
+{
+    double dtWater;
+    if (computeWater)
+    {
+        // the reference ignores run()'s error code (soilFluxes3D.cpp:1796)
+        waterMainLoop(maxTimeStep, dtWater);
+    }
+    else
+        dtWater = std::min(maxTimeStep, p->deltaTmax);
+    ++cnt.steps;
+    return dtWater;
+}
+
+// soilFluxes3D.cpp:1760-1777
+void Engine::computePeriod(double timePeriod)
+{
+    double sumCurrentTime = 0.;
+    curPeriod.waterSinkSource = 0.;
+    curPeriod.heatSinkSource = 0.;
+    while (sumCurrentTime < timePeriod)
+        sumCurrentTime += computeStep(timePeriod - sumCurrentTime);
+    if (computeWater) updateWaterBalanceDataWholePeriod();
+}
+
+// CPUSolver::waterMainLoop (cpusolver.cpp:143-190)
+bool Engine::waterMainLoop(double maxTimeStep, double &acceptedTimeStep)
+{
+    BalanceResult stepStatus = BalanceResult::Refused;
+    while (stepStatus != BalanceResult::Accepted)
+    {
+        acceptedTimeStep = std::min(p->deltaTcurr, maxTimeStep);
+        k_begin_try(v);                 // oldH = H ; x = H ; Se ; surface capacity
+        xcur = 0;
+        ++cnt.tries;
+
+        stepStatus = waterApproximationLoop(acceptedTimeStep);
+
+        if (stepStatus == BalanceResult::Nan) return false;
+        if (stepStatus != BalanceResult::Accepted) k_restore_old(v);
+    }
+    return true;
+}
+
+// CPUSolver::checkCourant, the time-step update after a failed test (cpusolver.cpp:262-278)
+bool Engine::courantFailed(double /*deltaT*/, double courant)
+{
+    p->deltaTcurr /= courant;
+    int multiply = 0;
+    while (p->deltaTcurr < 1.) { p->deltaTcurr *= 10.; ++multiply; }
+    p->deltaTcurr = floor(p->deltaTcurr);
+    for (int i = 0; i < multiply; i++) p->deltaTcurr /= 10.;
+    p->deltaTcurr = std::max(p->deltaTmin, p->deltaTcurr);
+    return true;
+}
+
+// CPUSolver::solveLinearSystem (cpusolver.cpp:672-703): the stopping rule runs on the device;
+// sweeps are enqueued in batches and the control block is read back once per batch.
+int Engine::solveWater(int approx)
+{
+    const int maxIter = (int)calcCurrentMaxIterationNumber(approx);
+    const int start = xcur;
+    int launched = 0;
+    Ctrl c{};
+    int batch = std::min(std::max(lastSweeps + 1, 4), 32);
+    for (;;)
+    {
+        const int n = std::min(batch, maxIter - launched);
+        for (int k = 0; k < n; ++k, ++launched)
+            k_jacobi(v, xbuf((start + launched) & 1), xbuf((start + launched + 1) & 1), maxIter, p->residualTolerance);
+        read_ctrl(v, &c);
+        if (c.status != SOLVE_RUNNING || launched >= maxIter) break;
+        batch = std::min(batch * 2, 32);
+    }
+    if (c.status != SOLVE_COURANT_FAIL)
+    {
+        xcur = (start + c.sweeps) & 1;
+        cnt.sweeps += (uint64_t)c.sweeps;
+        lastSweeps = c.sweeps;
+    }
+    courantWater = c.courantMax;
+    return c.status;
+}
+
+// CPUSolver::waterApproximationLoop (cpusolver.cpp:392-468)
+BalanceResult Engine::waterApproximationLoop(double deltaT)
+{
+    BalanceResult balanceResult = BalanceResult::Refused;
+    bestMBRerror = SF3D_NODATA;
+
+    for (int approxIdx = 0; approxIdx < (int)p->maxApproximationsNumber; ++approxIdx)
+    {
+        ++cnt.approximations;
+        k_node_phase(v, deltaT, 1);                             // computeCapacity + updateBoundaryWaterData
+        k_assemble(v, deltaT, approxIdx, p->deltaTmin);         // rows + Courant + normalisation
+        const int status = solveWater(approxIdx);
+
+        if (status == SOLVE_COURANT_FAIL)
+        {
+            courantFailed(deltaT, courantWater);
+            return BalanceResult::Halved;
+        }
+        const bool isStepValid = (status != SOLVE_DIVERGED);
+        if (!isStepValid && deltaT > p->deltaTmin)
+        {
+            p->deltaTcurr = std::max(p->deltaTmin, p->deltaTcurr / 2.);
+            return BalanceResult::Halved;
+        }
+
+        k_post(v, xbuf(xcur), deltaT, 0);                       // H = x ; Se ; storage ; sink sum
+        balanceResult = evaluateWaterBalance(approxIdx, deltaT);
+
+        if (balanceResult == BalanceResult::Accepted || balanceResult == BalanceResult::Halved
+            || balanceResult == BalanceResult::Nan)
+            return balanceResult;
+    }
+    return balanceResult;
+}
+
+// Water::computeCurrentMassBalance (water.cpp:96-123) from the two reduced sums
+void Engine::computeCurrentMassBalance(double deltaT, const Ctrl &c)
+{
+    Balance cur;
+    cur.waterStorage = c.storage;
+    const double deltaStorage = cur.waterStorage - prevStep.waterStorage;
+    cur.waterSinkSource = c.sinkSum;
+    cur.waterMBE = deltaStorage - cur.waterSinkSource;
+
+    const double timePercentage = 0.001 * std::max(deltaT, 30.0) / 3600.;
+    double minRefWaterStorage = cur.waterStorage * timePercentage;
+    minRefWaterStorage = std::max(minRefWaterStorage, 0.001);
+    const double referenceWater = std::max(fabs(cur.waterSinkSource), minRefWaterStorage);
+    cur.waterMBR = cur.waterMBE / referenceWater;
+
+    // balanceDataCurrentTimeStep = currentBalance copies the whole struct, heat fields included
+    // (default-initialised to 0 in the reference's local)
+    curStep = cur;
+}
+
+// Water::evaluateWaterBalance (water.cpp:165-227)
+BalanceResult Engine::evaluateWaterBalance(int approxNr, double deltaT)
+{
+    Ctrl c{};
+    read_ctrl(v, &c);
+    computeCurrentMassBalance(deltaT, c);
+
+    const double currMBRerror = fabs(curStep.waterMBR);
+
+    if (std::isnan(currMBRerror))
+    {
+        if (deltaT > p->deltaTmin)
+        {
+            p->deltaTcurr = std::max(p->deltaTcurr * 0.5, p->deltaTmin);
+            return BalanceResult::Halved;
+        }
+        else if (approxNr > 0)
+        {
+            restoreBestStep(deltaT);
+            acceptStep(deltaT);
+            return BalanceResult::Accepted;
+        }
+        return BalanceResult::Nan;
+    }
+
+    if (currMBRerror < p->MBRThreshold)
+    {
+        acceptStep(deltaT);
+        if (approxNr < 3 && currMBRerror < p->MBRThreshold * 0.1 && courantWater < p->CourantWaterThreshold)
+            p->deltaTcurr = std::min(p->deltaTmax, p->deltaTcurr * 2);
+        return BalanceResult::Accepted;
+    }
+
+    if (approxNr == 0 || currMBRerror < bestMBRerror)
+    {
+        dev_copy(v.bestH, v.H, (size_t)v.N * sizeof(double));
+        bestMBRerror = currMBRerror;
+    }
+
+    if (currMBRerror > (bestMBRerror * p->instabilityFactor) || approxNr == ((int)p->maxApproximationsNumber - 1))
+    {
+        if (deltaT > p->deltaTmin)
+        {
+            p->deltaTcurr = std::max(p->deltaTcurr * 0.5, p->deltaTmin);
+            return BalanceResult::Halved;
+        }
+        restoreBestStep(deltaT);
+        acceptStep(deltaT);
+        return BalanceResult::Accepted;
+    }
+    return BalanceResult::Refused;
+}
+
+// Water::acceptStep (water.cpp:230-251)
+void Engine::acceptStep(double deltaT)
+{
+    prevStep.waterStorage = curStep.waterStorage;
+    prevStep.waterSinkSource = curStep.waterSinkSource;
+    curPeriod.waterSinkSource += curStep.waterSinkSource;
+    k_accept(v, deltaT);
+}
+
+// Water::restoreBestStep (water.cpp:253-267)
+void Engine::restoreBestStep(double deltaT)
+{
+    k_restore_best(v);              // H = best ; Se
+    k_node_phase(v, deltaT, 0);     // K ; updateBoundaryWaterData
+    k_post(v, nullptr, deltaT, 2);  // storage ; sink sum
+    Ctrl c{};
+    read_ctrl(v, &c);
+    computeCurrentMassBalance(deltaT, c);
+}
+
+// Water::computeTotalWaterContent (water.cpp:71-90)
+double Engine::totalWaterContent()
+{
+    k_post(v, nullptr, 1., 2);
+    Ctrl c{};
+    read_ctrl(v, &c);
+    return c.storage;
+}
+
+double Engine::totalBoundaryWaterFlow(uint32_t boundaryType)
+{
+    k_total_boundary_flow(v, boundaryType);
+    Ctrl c{};
+    read_ctrl(v, &c);
+    return c.boundarySum;
+}
+
+// Water::initializeWaterBalance (water.cpp:35-65)
+uint8_t Engine::initializeWaterBalance()
+{
+    const double currentWC = totalWaterContent();
+    wholePeriod.waterStorage = currentWC;
+    curPeriod.waterStorage = currentWC;
+    curStep.waterStorage = currentWC;
+    prevStep.waterStorage = currentWC;
+    curStep.waterSinkSource = prevStep.waterSinkSource = curPeriod.waterSinkSource = wholePeriod.waterSinkSource = 0.;
+    curStep.waterMBR = wholePeriod.waterMBR = 0.;
+    curStep.waterMBE = wholePeriod.waterMBE = 0.;
+    dev_zero(v.lflow, (size_t)SF3D_NLINK * v.N * sizeof(double));
+    dev_zero(v.bSum, (size_t)v.N * sizeof(double));
+    return SF3D_OK;
+}
+
+// Water::updateWaterBalanceDataWholePeriod (water.cpp:143-156)
+void Engine::updateWaterBalanceDataWholePeriod()
+{
+    wholePeriod.waterSinkSource += curPeriod.waterSinkSource;
+    const double deltaStoragePeriod = curStep.waterStorage - curPeriod.waterStorage;
+    const double deltaStorageHistorical = curStep.waterStorage - wholePeriod.waterStorage;
+    curPeriod.waterMBE = deltaStoragePeriod - curPeriod.waterSinkSource;
+    wholePeriod.waterMBE = deltaStorageHistorical - wholePeriod.waterSinkSource;
+    const double referenceWater = std::max(0.001, wholePeriod.waterSinkSource);
+    wholePeriod.waterMBR = wholePeriod.waterMBE / referenceWater;
+    curPeriod.waterStorage = curStep.waterStorage;
+}
+
+}  // namespace sf3d

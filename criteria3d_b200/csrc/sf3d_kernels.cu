@@ -1,0 +1,612 @@
+// sf3d_kernels.cu -- hand-written sm_100a kernels of the soilFluxes3D water time step and the
+// device services behind sf3d_backend.h.
+//
+// All kernels are HBM-bandwidth bound sparse-stencil / streaming passes over structure-of-arrays
+// state (no tensor cores: there is no dense contraction on this path).  Common shape:
+//   * grid-stride loop, 256 threads per block, grid = min(ceil(n/256), 148 SMs x 8) so that the
+//     grid is a whole number of waves on a B200 and the per-block partials stay small;
+//   * consecutive threads own consecutive nodes -> every array access is a coalesced 256 B
+//     request; neighbour gathers (x[j], H[j], K[j]) hit L1/L2 because links connect index
+//     neighbours (+-1, +-cols, +-layer stride);
+//   * reductions: warp shuffles -> shared memory -> one partial per block -> the LAST block
+//     (atomic ticket) folds the partials in a fixed order and writes the scalar into the device
+//     control block.  Deterministic for a given grid; no host round trip per reduction;
+//   * the Jacobi sweep evaluates the reference's stopping rule on the device (last block), so a
+//     batch of sweeps can be enqueued without synchronising; sweeps launched after convergence
+//     return immediately.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "sf3d_backend.h"
+#include "sf3d_rows_heat.h"
+
+namespace sf3d {
+
+#define SF3D_BLOCK 256
+#define SF3D_MAX_BLOCKS (148 * 8)
+
+static cudaStream_t g_stream = nullptr;
+static int g_device = -1;
+static uint64_t g_launches = 0;
+static Ctrl *g_ctrlPinned = nullptr;
+
+#define CUDA_OK(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            fprintf(stderr, "[sf3d_b200] CUDA error %d (%s) at %s:%d: %s\n", (int)e_,          \
+                    cudaGetErrorString(e_), __FILE__, __LINE__, #call);                        \
+            throw DeviceError{(int)e_, cudaGetErrorString(e_), #call};                         \
+        }                                                                                      \
+    } while (0)
+
+#define LAUNCH_CHECK()                                                                         \
+    do { ++g_launches; CUDA_OK(cudaGetLastError()); } while (0)
+
+static void ensure_device();
+// ---- optional per-launch timing (CUDA events on the library's stream) ----------------------
+struct ProfRec { int kind; cudaEvent_t a, b; };
+static bool g_prof = false;
+static std::vector<ProfRec> g_pending;
+static std::vector<cudaEvent_t> g_eventPool;
+static double g_profMs[SF3D_K_COUNT];
+static uint64_t g_profN[SF3D_K_COUNT];
+
+static cudaEvent_t prof_event()
+{
+    if (!g_eventPool.empty()) { cudaEvent_t e = g_eventPool.back(); g_eventPool.pop_back(); return e; }
+    cudaEvent_t e; CUDA_OK(cudaEventCreate(&e)); return e;
+}
+static void prof_resolve()          // call only when the stream is idle
+{
+    for (const ProfRec &r : g_pending)
+    {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { g_profMs[r.kind] += ms; g_profN[r.kind] += 1; }
+        g_eventPool.push_back(r.a); g_eventPool.push_back(r.b);
+    }
+    g_pending.clear();
+}
+struct ProfScope {
+    int kind; cudaEvent_t a{}, b{}; bool on;
+    explicit ProfScope(int k) : kind(k), on(g_prof)
+    { if (on) { a = prof_event(); b = prof_event(); cudaEventRecord(a, g_stream); } }
+    ~ProfScope() { if (on) { cudaEventRecord(b, g_stream); g_pending.push_back(ProfRec{kind, a, b}); } }
+};
+void prof_enable(bool on)
+{
+    ensure_device();
+    CUDA_OK(cudaStreamSynchronize(g_stream));
+    prof_resolve();
+    g_prof = on;
+    for (int k = 0; k < SF3D_K_COUNT; ++k) { g_profMs[k] = 0.; g_profN[k] = 0; }
+}
+void prof_get(double ms[SF3D_K_COUNT], uint64_t n[SF3D_K_COUNT])
+{
+    ensure_device();
+    CUDA_OK(cudaStreamSynchronize(g_stream));
+    prof_resolve();
+    for (int k = 0; k < SF3D_K_COUNT; ++k) { ms[k] = g_profMs[k]; n[k] = g_profN[k]; }
+}
+
+void dev_select(int device)
+{
+    if (g_stream && device == g_device) return;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+    {
+        fprintf(stderr, "[sf3d_b200] no CUDA device available (%s). The B200 product has no CPU fallback.\n",
+                cudaGetErrorString(e));
+        throw DeviceError{(int)e, "no CUDA device", "dev_select"};
+    }
+    if (device < 0 || device >= count) throw DeviceError{-1, "bad device index", "dev_select"};
+    CUDA_OK(cudaSetDevice(device));
+    if (g_stream) { cudaStreamDestroy(g_stream); g_stream = nullptr; }
+    CUDA_OK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    if (!g_ctrlPinned) CUDA_OK(cudaMallocHost((void **)&g_ctrlPinned, sizeof(Ctrl)));
+    g_device = device;
+}
+int dev_current() { return g_device; }
+static void ensure_device() { if (!g_stream) dev_select(g_device < 0 ? 0 : g_device); }
+
+void *dev_alloc(size_t bytes)
+{
+    ensure_device();
+    void *p = nullptr;
+    if (bytes == 0) bytes = 8;
+    CUDA_OK(cudaMalloc(&p, bytes));
+    CUDA_OK(cudaMemsetAsync(p, 0, bytes, g_stream));
+    return p;
+}
+void dev_free(void *p) { if (p) cudaFree(p); }
+void dev_zero(void *p, size_t bytes) { ensure_device(); CUDA_OK(cudaMemsetAsync(p, 0, bytes, g_stream)); }
+void dev_copy(void *dst, const void *src, size_t bytes)
+{ ensure_device(); CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, g_stream)); }
+void h2d(void *dst, const void *src, size_t bytes)
+{ ensure_device(); CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_stream)); CUDA_OK(cudaStreamSynchronize(g_stream)); }
+void d2h(void *dst, const void *src, size_t bytes)
+{ ensure_device(); CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_stream)); CUDA_OK(cudaStreamSynchronize(g_stream)); }
+void *pinned_alloc(size_t bytes) { ensure_device(); void *p = nullptr; CUDA_OK(cudaMallocHost(&p, bytes)); return p; }
+void pinned_free(void *p) { if (p) cudaFreeHost(p); }
+void dev_sync() { ensure_device(); CUDA_OK(cudaStreamSynchronize(g_stream)); }
+uint64_t launches() { return g_launches; }
+void *dev_stream() { ensure_device(); return (void *)g_stream; }
+
+int reduce_blocks(uint32_t n)
+{
+    long b = ((long)n + SF3D_BLOCK - 1) / SF3D_BLOCK;
+    if (b < 1) b = 1;
+    if (b > SF3D_MAX_BLOCKS) b = SF3D_MAX_BLOCKS;
+    return (int)b;
+}
+
+// ------------------------------------------------------------------------------------------
+// reduction helpers
+// ------------------------------------------------------------------------------------------
+template <bool IS_MAX>
+__device__ __forceinline__ double warp_reduce(double v)
+{
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        const double other = __shfl_down_sync(0xffffffffu, v, o);
+        v = IS_MAX ? ((v < other) ? other : v) : (v + other);
+    }
+    return v;
+}
+
+// result valid in thread 0
+template <bool IS_MAX>
+__device__ __forceinline__ double block_reduce(double v, double *sh)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_reduce<IS_MAX>(v);
+    __syncthreads();
+    if (lane == 0) sh[wid] = v;
+    __syncthreads();
+    if (wid == 0)
+    {
+        v = (lane < (SF3D_BLOCK / 32)) ? sh[lane] : 0.0;   // identities: 0 for + and for max of non-negatives
+        v = warp_reduce<IS_MAX>(v);
+    }
+    return v;
+}
+
+// elects the last block of the grid to finish; all its threads return true
+__device__ __forceinline__ bool last_block(Ctrl *c)
+{
+    __shared__ int isLast;
+    __threadfence();
+    if (threadIdx.x == 0)
+    {
+        const unsigned t = atomicAdd(&c->ticket, 1u);
+        isLast = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    return isLast != 0;
+}
+
+// fold gridDim.x partials in a fixed order; result valid in thread 0
+template <bool IS_MAX>
+__device__ __forceinline__ double fold_partials(const double *part, double *sh)
+{
+    double acc = 0.0;
+    for (unsigned k = threadIdx.x; k < gridDim.x; k += SF3D_BLOCK)
+    {
+        const double p = __ldcg(part + k);
+        acc = IS_MAX ? ((acc < p) ? p : acc) : (acc + p);
+    }
+    return block_reduce<IS_MAX>(acc, sh);
+}
+
+// ------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SF3D_BLOCK) kern_link_geometry(SF3DView v, int *orderOk)
+{
+    const size_t N = v.N;
+    for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
+    {
+        const uint32_t m = v.meta[i];
+        if ((META_SURFACE(m) != 0) != (i < v.Ns)) *orderOk = 0;
+        #pragma unroll
+        for (int c = 0; c < SF3D_NLINK; ++c)
+        {
+            const int slot = sf3d_slot_of_col(c);
+            uint32_t j = i;
+            double d = 0.;
+            if (META_HAS_SLOT(m, slot))
+            {
+                j = v.lidx[(size_t)slot * N + i];
+                d = sf3d_link_distance(v, i, j, slot);
+            }
+            v.mcol[(size_t)c * N + i] = j;
+            v.ldist[(size_t)slot * N + i] = d;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SF3D_BLOCK) kern_begin_try(SF3DView v)
+{
+    for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
+        sf3d_row_begin_try(v, i);
+}
+
+__global__ void __launch_bounds__(SF3D_BLOCK) kern_restore_old(SF3DView v)
+{
+    for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
+        sf3d_row_restore_old(v, i);
+}
+
+__global__ void __launch_bounds__(SF3D_BLOCK) kern_node_phase(SF3DView v, double dt, int withCapacity)
+{
+    for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
+        sf3d_row_node_phase(v, i, dt, withCapacity);
+}
+
+// link phase: conductances, diagonal, row normalisation, right-hand side, per-row Courant;
+// the last block publishes max Courant and arms the on-device solver state
+// (CPUSolver::checkCourant test, cpusolver.cpp:248-260)
+__global__ void __launch_bounds__(SF3D_BLOCK) kern_assemble(SF3DView v, double dt, int approx, double dtMin)
+{
+    __shared__ double sh[SF3D_BLOCK / 32];
+    double courant = 0.;
+    for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
+    {
+        const double c = sf3d_row_assemble(v, i, dt, approx);
+        courant = (courant < c) ? c : courant;
+    }
+    courant = block_reduce<true>(courant, sh);
+    if (threadIdx.x == 0) v.partA[blockIdx.x] = courant;
+    if (last_block(v.ctrl))
+    {
+        const double cmax = fold_partials<true>(v.partA, sh);
+        if (threadIdx.x == 0)
+        {
+            Ctrl *c = v.ctrl;
+            c->courantMax = cmax;
+            const bool ok = (cmax < 1.01) || (dt <= dtMin);
+            c->status = ok ? SOLVE_RUNNING : SOLVE_COURANT_FAIL;
+            c->sweeps = 0;
+            c->bestNorm = 1.;       // solveLinearSystem: bestErrorNorm = 1 (cpusolver.cpp:674)
+            c->lastNorm = 0.;
+            c->ticket = 0;
+        }
+    }
+}
+
+// one Jacobi sweep (Water::JacobiWaterCPU) + the stopping rule of CPUSolver::solveLinearSystem
+// (cpusolver.cpp:678-700) evaluated by the last block
+__global__ void __launch_bounds__(SF3D_BLOCK) kern_jacobi(SF3DView v, const double *__restrict__ xin,
+                                                          double *__restrict__ xout, int maxIter, double tol)
+{
+    if (v.ctrl->status != SOLVE_RUNNING) return;
+    __shared__ double sh[SF3D_BLOCK / 32];
+    double norm = 0.;
+    for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
+        norm += sf3d_row_jacobi(v, i, xin, xout);
+    norm = block_reduce<false>(norm, sh);
+    if (threadIdx.x == 0) v.partA[blockIdx.x] = norm;
+    if (last_block(v.ctrl))
+    {
+        const double total = fold_partials<false>(v.partA, sh);
+        if (threadIdx.x == 0)
+        {
+            Ctrl *c = v.ctrl;
+            const double curr = total / v.N;                      // water.cpp:600
+            c->lastNorm = curr;
+            c->sweeps += 1;
+            if (curr < tol) c->status = SOLVE_CONVERGED;          // cpusolver.cpp:692
+            else if (curr > c->bestNorm * 10) c->status = SOLVE_DIVERGED;   // :695
+            else
+            {
+                if (curr < c->bestNorm) c->bestNorm = curr;       // :698
+                if (c->sweeps >= maxIter) c->status = SOLVE_MAXITER;
+            }
+            c->ticket = 0;
+        }
+    }
+}
+
+// H = x, Se refresh, and the two mass-balance sums
+__global__ void __launch_bounds__(SF3D_BLOCK) kern_post(SF3DView v, const double *__restrict__ x, double dt, int mode)
+{
+    __shared__ double sh[SF3D_BLOCK / 32];
+    double storage = 0., sinkSum = 0.;
+    for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
+    {
+        double s, q;
+        sf3d_row_post(v, i, x, dt, mode, &s, &q);
+        storage += s;
+        sinkSum += q;
+    }
+    storage = block_reduce<false>(storage, sh);
+    sinkSum = block_reduce<false>(sinkSum, sh);
+    if (threadIdx.x == 0) { v.partA[blockIdx.x] = storage; v.partB[blockIdx.x] = sinkSum; }
+    if (last_block(v.ctrl))
+    {
+        const double st = fold_partials<false>(v.partA, sh);
+        const double sk = fold_partials<false>(v.partB, sh);
+        if (threadIdx.x == 0) { v.ctrl->storage = st; v.ctrl->sinkSum = sk; v.ctrl->ticket = 0; }
+    }
+}
+
+__global__ void __launch_bounds__(SF3D_BLOCK) kern_accept(SF3DView v, double dt)
+{
+    for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
+        sf3d_row_accept(v, i, dt);
+}
+
+__global__ void __launch_bounds__(SF3D_BLOCK) kern_restore_best(SF3DView v)
+{
+    for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
+        sf3d_row_restore_best(v, i);
+}
+
+// getTotalBoundaryWaterFlow (soilFluxes3D.cpp:1240-1250)
+__global__ void __launch_bounds__(SF3D_BLOCK) kern_total_boundary(SF3DView v, uint32_t bt)
+{
+    __shared__ double sh[SF3D_BLOCK / 32];
+    double sum = 0.;
+    for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
+        if (META_BT(v.meta[i]) == bt) sum += v.bSum[i];
+    sum = block_reduce<false>(sum, sh);
+    if (threadIdx.x == 0) v.partA[blockIdx.x] = sum;
+    if (last_block(v.ctrl))
+    {
+        const double t = fold_partials<false>(v.partA, sh);
+        if (threadIdx.x == 0) { v.ctrl->boundarySum = t; v.ctrl->ticket = 0; }
+    }
+}
+
+// setNodeMatricPotential / setNodeTotalPotential over a range (soilFluxes3D.cpp:869-906)
+__global__ void __launch_bounds__(SF3D_BLOCK) kern_set_potential(SF3DView v, uint32_t first, uint32_t count,
+                                                                 const double *__restrict__ src, int isTotal)
+{
+    for (uint32_t k = blockIdx.x * SF3D_BLOCK + threadIdx.x; k < count; k += gridDim.x * SF3D_BLOCK)
+    {
+        const uint32_t i = first + k;
+        const double z = v.z[i];
+        const double H = isTotal ? src[k] : z + src[k];
+        v.H[i] = H;
+        v.oldH[i] = H;
+        if (META_SURFACE(v.meta[i])) { v.Se[i] = 1.; v.K[i] = SF3D_NODATA; }
+        else
+        {
+            const SoilRec &s = v.soil[v.tab[i]];
+            const double se = sf3d_node_se(s, v.wrcModel, H, z);
+            v.Se[i] = se;
+            double K = sf3d_mualem(s, v.wrcModel, se);
+            if (v.computeHeat && v.computeHeatVapor) K += sf3d_heat_vapor_K(v, i);
+            v.K[i] = K;
+        }
+    }
+}
+
+// bulk getters: same value as the scalar getter of each node (soilFluxes3D.cpp:951-1234)
+__global__ void __launch_bounds__(SF3D_BLOCK) kern_get_field(SF3DView v, int field, uint32_t first, uint32_t count,
+                                                             double *__restrict__ dst)
+{
+    const size_t N = v.N;
+    for (uint32_t k = blockIdx.x * SF3D_BLOCK + threadIdx.x; k < count; k += gridDim.x * SF3D_BLOCK)
+    {
+        const uint32_t i = first + k;
+        const uint32_t m = v.meta[i];
+        const bool surface = META_SURFACE(m);
+        double r = -1111.;
+        switch (field)
+        {
+            case SF3D_F_WATER_CONTENT:
+                r = surface ? (v.H[i] - v.z[i]) : sf3d_theta_from_se(v.soil[v.tab[i]], v.Se[i]);
+                break;
+            case SF3D_F_DEGREE_OF_SATURATION:
+                if (!surface) r = v.Se[i];
+                else
+                {
+                    const double curPot = v.H[i] - v.z[i], maxPot = 0.001;
+                    r = curPot <= 0 ? 0 : (curPot > maxPot ? 1. : curPot / maxPot);
+                }
+                break;
+            case SF3D_F_WATER_CONDUCTIVITY: r = v.K[i]; break;
+            case SF3D_F_MATRIC_POTENTIAL:   r = v.H[i] - v.z[i]; break;
+            case SF3D_F_TOTAL_POTENTIAL:    r = v.H[i]; break;
+            case SF3D_F_POND:               r = surface ? v.pond[i] : -1111.; break;
+            case SF3D_F_BOUNDARY_WATER_FLOW: r = (META_BT(m) == BT_NONE) ? -4444. : v.bSum[i]; break;
+            case SF3D_F_SUM_LATERAL_FLOW:
+            {
+                double s = 0.;
+                for (uint32_t l = 0; l < META_NLAT(m); ++l) s += v.lflow[(size_t)(2 + l) * N + i];
+                r = s;
+                break;
+            }
+            case SF3D_F_MAX_FLOW_UP:   r = v.lflow[i]; break;
+            case SF3D_F_MAX_FLOW_DOWN: r = v.lflow[N + i]; break;
+            case SF3D_F_MAX_FLOW_LATERAL:
+            {
+                double mx = 0.;
+                for (uint32_t l = 0; l < META_NLAT(m); ++l) mx = sf3d_max(mx, v.lflow[(size_t)(2 + l) * N + i]);
+                r = mx;
+                break;
+            }
+            case SF3D_F_TEMPERATURE:
+                r = (v.computeHeat && !surface) ? v.T[i] : -3333.;
+                break;
+            default: break;
+        }
+        dst[k] = r;
+    }
+}
+
+// DEM -> node/link graph (Project3D::setCrit3DTopography + setCrit3DNodeSoil,
+// src/project3D/project3D.cpp:941-1103, 1164-1238), one thread per (layer, cell)
+__global__ void __launch_bounds__(SF3D_BLOCK) kern_build_grid(SF3DView v, GridDev g)
+{
+    const size_t N = v.N;
+    const uint64_t cells = (uint64_t)g.rows * g.cols;
+    const uint64_t total = cells * g.layers;
+    const double area = g.cell * g.cell;
+    for (uint64_t t = (uint64_t)blockIdx.x * SF3D_BLOCK + threadIdx.x; t < total; t += (uint64_t)gridDim.x * SF3D_BLOCK)
+    {
+        const uint32_t layer = (uint32_t)(t / cells);
+        const uint64_t cell = t % cells;
+        const int32_t rank = g.rank[cell];
+        if (rank < 0) continue;
+        const uint32_t row = (uint32_t)(cell / g.cols), col = (uint32_t)(cell % g.cols);
+        const uint32_t i = layer * g.nValid + (uint32_t)rank;
+
+        const double thickness = g.layerThickness[layer];
+        const double volume = area * thickness;
+        const float lateralArea = (layer == 0) ? (float)g.cell : (float)(g.cell * thickness);
+        const float bSlopeF = g.slope ? g.slope[cell] : 0.f;
+        const float zf = g.dem[cell] - (float)g.layerDepth[layer];
+        const bool outlet = g.outlet && g.outlet[cell];
+
+        v.x[i] = g.xll + g.cell * ((double)col + 0.5);
+        v.y[i] = g.yll + g.cell * ((double)(g.rows - row) - 0.5);
+        v.z[i] = (double)zf;
+
+        uint32_t bt = BT_NONE;
+        double bSlope = 0., bSize = 0.;
+        const bool surface = (layer == 0);
+        if (surface)
+        {
+            v.size[i] = area;
+            if (outlet && g.freeRunoff) { bt = BT_RUNOFF; bSlope = bSlopeF; bSize = (double)(float)g.cell; }
+        }
+        else
+        {
+            v.size[i] = volume;
+            if (layer == g.layers - 1) { if (g.freeBottom) { bt = BT_FREE_DRAINAGE; bSlope = 0.; bSize = (double)(float)area; } }
+            else if (outlet && g.freeLateral) { bt = BT_FREE_LATERAL; bSlope = bSlopeF; bSize = (double)lateralArea; }
+            else if (layer == 1 && g.boundaryL1) bt = g.boundaryL1[cell];
+        }
+        if (bt != BT_NONE)          // setNodeBoundary (soilFluxes3D.cpp:689-725)
+        {
+            v.bSlope[i] = bSlope; v.bSize[i] = bSize;
+            v.bRate[i] = 0.; v.bSum[i] = 0.; v.bPresc[i] = SF3D_NODATA;
+        }
+        v.sink[i] = 0.;
+
+        // links: slot 0 Up, slot 1 Down, slots 2.. Lateral in (dr,dc) order (-1,-1) .. (1,1)
+        uint32_t mask = 0, nLat = 0;
+        if (layer > 0)
+        {
+            v.lidx[i] = (layer - 1) * g.nValid + (uint32_t)rank;
+            v.larea[i] = area; mask |= 1u;
+        }
+        if (layer < g.layers - 1)
+        {
+            v.lidx[N + i] = (layer + 1) * g.nValid + (uint32_t)rank;
+            v.larea[N + i] = area; mask |= 2u;
+        }
+        for (int di = -1; di <= 1; ++di)
+        for (int dj = -1; dj <= 1; ++dj)
+        {
+            if (di == 0 && dj == 0) continue;
+            const long rr = (long)row + di, cc = (long)col + dj;
+            if (rr < 0 || cc < 0 || rr >= (long)g.rows || cc >= (long)g.cols) continue;
+            const int32_t lrank = g.rank[(uint64_t)rr * g.cols + (uint64_t)cc];
+            if (lrank < 0) continue;
+            const uint32_t slot = 2 + nLat;
+            v.lidx[(size_t)slot * N + i] = layer * g.nValid + (uint32_t)lrank;
+            v.larea[(size_t)slot * N + i] = lateralArea * 0.5;
+            mask |= (1u << slot);
+            ++nLat;
+        }
+        v.meta[i] = bt | ((surface ? 1u : 0u) << 4) | (nLat << 5) | (mask << 9);
+
+        if (surface)
+        {
+            v.tab[i] = g.surfaceId ? g.surfaceId[cell] : 0;
+            v.pond[i] = g.pond ? g.pond[cell] : (double)0.0001f;
+        }
+        else
+        {
+            const uint32_t sid = g.soilId ? g.soilId[cell] : 0;
+            v.tab[i] = g.layerTab[(size_t)layer * g.nSoilIds + sid];
+            if (g.computeHeat) { v.T[i] = 293.15; v.oldT[i] = 293.15; v.hFlux[i] = 0.; v.hSink[i] = 0.; }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SF3D_BLOCK) kern_count_links(SF3DView v, unsigned long long *out)
+{
+    unsigned long long n = 0;
+    for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
+        n += __popc(META_LINKMASK(v.meta[i]));
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_down_sync(0xffffffffu, n, o);
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(out, n);
+}
+
+__global__ void kern_fill(double *p, size_t n, double value)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = value;
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+#define GRID(n) reduce_blocks(n), SF3D_BLOCK, 0, g_stream
+
+void dev_fill_f64(double *p, size_t n, double value)
+{ ensure_device(); kern_fill<<<reduce_blocks((uint32_t)(n > 0xFFFFFFFFull ? 0xFFFFFFFFull : n)), 256, 0, g_stream>>>(p, n, value); LAUNCH_CHECK(); }
+
+void k_link_geometry(const SF3DView &v, int *surfaceOrderOk)
+{
+    int *flag = (int *)dev_alloc(sizeof(int));
+    const int one = 1;
+    h2d(flag, &one, sizeof one);
+    kern_link_geometry<<<GRID(v.N)>>>(v, flag); LAUNCH_CHECK();
+    d2h(surfaceOrderOk, flag, sizeof(int));
+    dev_free(flag);
+}
+void k_begin_try(const SF3DView &v) { ProfScope ps(SF3D_K_BEGIN_TRY); kern_begin_try<<<GRID(v.N)>>>(v); LAUNCH_CHECK(); }
+void k_restore_old(const SF3DView &v) { ProfScope ps(SF3D_K_OTHER); kern_restore_old<<<GRID(v.N)>>>(v); LAUNCH_CHECK(); }
+void k_node_phase(const SF3DView &v, double dt, int withCapacity) { ProfScope ps(SF3D_K_NODE_PHASE); kern_node_phase<<<GRID(v.N)>>>(v, dt, withCapacity); LAUNCH_CHECK(); }
+void k_assemble(const SF3DView &v, double dt, int approx, double dtMin) { ProfScope ps(SF3D_K_ASSEMBLE); kern_assemble<<<GRID(v.N)>>>(v, dt, approx, dtMin); LAUNCH_CHECK(); }
+void k_jacobi(const SF3DView &v, const double *xin, double *xout, int maxIter, double tol)
+{ ProfScope ps(SF3D_K_JACOBI); kern_jacobi<<<GRID(v.N)>>>(v, xin, xout, maxIter, tol); LAUNCH_CHECK(); }
+void k_post(const SF3DView &v, const double *x, double dt, int mode) { ProfScope ps(SF3D_K_POST); kern_post<<<GRID(v.N)>>>(v, x, dt, mode); LAUNCH_CHECK(); }
+void k_accept(const SF3DView &v, double dt) { ProfScope ps(SF3D_K_ACCEPT); kern_accept<<<GRID(v.N)>>>(v, dt); LAUNCH_CHECK(); }
+void k_restore_best(const SF3DView &v) { ProfScope ps(SF3D_K_OTHER); kern_restore_best<<<GRID(v.N)>>>(v); LAUNCH_CHECK(); }
+void k_total_boundary_flow(const SF3DView &v, uint32_t bt) { kern_total_boundary<<<GRID(v.N)>>>(v, bt); LAUNCH_CHECK(); }
+void k_set_potential(const SF3DView &v, uint32_t first, uint32_t count, const double *src, int isTotal)
+{ if (count) { kern_set_potential<<<GRID(count)>>>(v, first, count, src, isTotal); LAUNCH_CHECK(); } }
+void k_get_field(const SF3DView &v, int field, uint32_t first, uint32_t count, double *dst)
+{ if (count) { kern_get_field<<<GRID(count)>>>(v, field, first, count, dst); LAUNCH_CHECK(); } }
+void k_build_grid(const SF3DView &v, const GridDev &g)
+{
+    const uint64_t total = (uint64_t)g.rows * g.cols * g.layers;
+    kern_build_grid<<<reduce_blocks((uint32_t)(total > 0xFFFFFFFFull ? 0xFFFFFFFFull : total)), SF3D_BLOCK, 0, g_stream>>>(v, g);
+    LAUNCH_CHECK();
+}
+
+uint64_t k_count_links(const SF3DView &v)
+{
+    unsigned long long *d = (unsigned long long *)dev_alloc(sizeof(unsigned long long));
+    kern_count_links<<<GRID(v.N)>>>(v, d); LAUNCH_CHECK();
+    unsigned long long h = 0;
+    d2h(&h, d, sizeof h);
+    dev_free(d);
+    return (uint64_t)h;
+}
+
+void read_ctrl(const SF3DView &v, Ctrl *out)
+{
+    ensure_device();
+    CUDA_OK(cudaMemcpyAsync(g_ctrlPinned, v.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, g_stream));
+    CUDA_OK(cudaStreamSynchronize(g_stream));
+    if (g_prof && g_pending.size() > 4096) prof_resolve();
+    *out = *g_ctrlPinned;
+}
+void write_ctrl(const SF3DView &v, const Ctrl *in)
+{
+    ensure_device();
+    CUDA_OK(cudaMemcpyAsync(v.ctrl, in, sizeof(Ctrl), cudaMemcpyHostToDevice, g_stream));
+    CUDA_OK(cudaStreamSynchronize(g_stream));
+}
+
+}  // namespace sf3d

@@ -1,0 +1,116 @@
+// sf3d_view.h -- data layout of the soilFluxes3D state in HBM (structure of arrays) and the
+// plain-old-data "view" that every kernel receives by value.
+//
+// Reference layout being replaced: nodesData_t / linkData_t[10] / boundaryData_t / waterData_t /
+// heatData_t (agrolib/soilFluxes3D/types.h:136-284) plus the row-pointer ELL matrix MatrixCPU
+// (types_cpu.h:7-20).  Here every quantity is one contiguous device array of length N (nodes)
+// or 10 x N (link slots, slot-major), so that a warp touching 32 consecutive nodes issues fully
+// coalesced 256-byte requests.  Surface nodes occupy [0, nSurface) as in the reference
+// (cpusolver.cpp:151,166,413,426).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SF3D_HD __host__ __device__ __forceinline__
+#else
+#define SF3D_HD inline
+#endif
+
+#define SF3D_NLINK 10           // maxTotalLink, types.h:25
+#define SF3D_NODATA (-9999.0)   // commonConstants.h:31
+
+// boundaryType_t values (types.h:98-99)
+enum : uint32_t { BT_NONE = 0, BT_RUNOFF = 1, BT_FREE_DRAINAGE = 2, BT_FREE_LATERAL = 3, BT_PRESCRIBED = 4,
+                  BT_URBAN = 5, BT_ROAD = 6, BT_CULVERT = 7, BT_HEAT_SURFACE = 8, BT_SOLUTE = 9 };
+
+// meta word per node:  bits 0-3 boundary type | bit 4 surface flag | bits 5-8 numLateralLink |
+//                      bits 9-18 link-present mask in SLOT order (slot 0 Up, 1 Down, 2.. Lateral)
+#define META_BT(m)        ((m) & 0xFu)
+#define META_SURFACE(m)   (((m) >> 4) & 1u)
+#define META_NLAT(m)      (((m) >> 5) & 0xFu)
+#define META_LINKMASK(m)  (((m) >> 9) & 0x3FFu)
+#define META_HAS_SLOT(m, s) (((m) >> (9 + (s))) & 1u)
+
+// Matrix columns are stored in the reference's COLUMN order, which fixes the floating-point
+// summation order of the Jacobi row (cpusolver.cpp:352-374): column 0 = Up (slot 0),
+// columns 1..8 = Lateral 0..7 (slots 2..9), column 9 = Down (slot 1).
+SF3D_HD int sf3d_slot_of_col(int c) { return c == 0 ? 0 : (c == 9 ? 1 : c + 1); }
+SF3D_HD int sf3d_col_of_slot(int s) { return s == 0 ? 0 : (s == 1 ? 9 : s - 1); }
+
+// soil horizon record (soilData_t, types.h:104-121) + constants hoisted out of the node loop
+struct SoilRec {
+    double alpha, n, m, he, Sc, thetaS, thetaR, Ksat, L, organicMatter, clay;
+    double invM;        // 1 / m                               (soilPhysics.cpp:186)
+    double invSc;       // 1 / Sc                              (soilPhysics.cpp:110)
+    double ScPowInvM;   // pow(Sc, 1/m)                        (soilPhysics.cpp:203)
+    double tDen;        // 1 - pow(1 - pow(Sc,1/m), m)         (soilPhysics.cpp:206)
+};
+
+struct CulvertRec { double width, height, roughness; };   // culvertData_t, types.h:159-164
+
+struct SolverParams {           // SolverParameters, types.h:291-315
+    double MBRThreshold, residualTolerance;
+    double deltaTmin, deltaTmax, deltaTcurr;
+    uint16_t maxApproximationsNumber, maxIterationsNumber;
+    uint8_t wrcModel, meanType;
+    double lateralVerticalRatio, heatWeightFactor;
+    double CourantWaterThreshold, instabilityFactor;
+};
+
+// device control block: scalars produced by reductions and the on-device solver state
+enum : int { SOLVE_RUNNING = 0, SOLVE_CONVERGED = 1, SOLVE_DIVERGED = 2, SOLVE_MAXITER = 3, SOLVE_COURANT_FAIL = 4 };
+struct Ctrl {
+    double courantMax;      // nodeGrid.CourantWater
+    double storage;         // sum theta*V            (water.cpp:71-90)
+    double sinkSum;         // sum waterFlow*dt       (water.cpp:130-140)
+    double lastNorm;        // JacobiWaterCPU return value of the last sweep
+    double bestNorm;        // solveLinearSystem bestErrorNorm
+    double heatCourantMax;  // updateBoundaryHeatData
+    double heatStorage, heatSinkSum;
+    double boundarySum;     // getTotalBoundaryWaterFlow
+    int    status;          // SOLVE_*
+    int    sweeps;          // sweeps executed in the current solve
+    unsigned int ticket;    // last-block election counter
+    int    pad;
+};
+
+struct SF3DView {
+    uint32_t N, Ns;                 // nodes, surface nodes
+    // flags (simulationFlags_t, types.h:188-197)
+    int computeHeat, computeHeatVapor, computeHeatAdvection, hfSaveMode;
+    // solver parameters needed on device
+    int wrcModel, meanType;
+    double lvRatio, heatWF;
+
+    // topology
+    double *x, *y, *z, *size;
+    uint32_t *meta;                 // packed, see META_*
+    uint16_t *tab;                  // soil-table / surface-table index
+    // boundary
+    double *bSlope, *bSize, *bRate, *bSum, *bPresc;
+    // links, slot-major: [slot*N + i]
+    uint32_t *lidx;
+    double *larea, *lflow;
+    double *ldist;                  // static link geometry (see k_link_geometry)
+    // water state
+    double *H, *oldH, *bestH, *Se, *SeOld, *K, *wFlow, *sink, *pond, *inv;
+    // linear system, COLUMN-major: [col*N + i]; mcol is static
+    uint32_t *mcol;
+    double *mval;
+    double *b, *cap, *x0, *x1;
+    // tables
+    const SoilRec *soil;
+    const double *rough;
+    const CulvertRec *culverts;     // null when no culvert is defined
+    const uint32_t *culvertOf;      // [Ns] index into culverts
+    // heat (null when !computeHeat)
+    double *T, *oldT, *hFlux, *hSink;
+    double *hbHeightWind, *hbHeightT, *hbRough, *hbAero, *hbSoilCond, *hbT, *hbRH, *hbWind, *hbNetIrr;
+    double *hbSens, *hbLat, *hbRad, *hbAdv, *hbFixT, *hbFixDepth;
+    double *lwFlux, *lvFlux;        // per link, slot-major (float-rounded values, heat.cpp:126-127)
+    double *lfluxes;                // [type][slot][i], types allocated per hfSaveMode
+    double *hdiag;                  // heat matrix diagonal (kept, cpusolver.cpp:561-567)
+    // control / reduction scratch
+    Ctrl *ctrl;
+    double *partA, *partB, *partC;  // per-block partials
+};

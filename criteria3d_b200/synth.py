@@ -189,6 +189,7 @@ def setup(sf: SoilFluxes3D, cat: Catchment, threads: int = 0,
           numerics: tuple | None = None) -> None:
     """initialize3DModel's call sequence (project3D.cpp:456-616) on implementation `sf`."""
     hf = HeatFluxSaveMode.Total if cat.heat else HeatFluxSaveMode.None_
+    sf.reset_solver()       # same starting deltaTcurr as a fresh process (see sf3d_ext_reset_solver)
     _ok(sf.initializeSF3D(cat.n_nodes, cat.n_surface, 8, True, cat.heat, False, int(hf)), "initializeSF3D")
     for i, (rough, _pond) in enumerate(SURFACE_TABLE):
         _ok(sf.setSurfaceProperties(i, rough), "setSurfaceProperties")

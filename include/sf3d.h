@@ -237,6 +237,7 @@ typedef struct sf3d_counters {
     double   last_courant;     /* nodeGrid.CourantWater                                    */
     double   last_mbr;         /* balanceDataCurrentTimeStep.waterMBR                      */
     double   last_mbe;         /* balanceDataCurrentTimeStep.waterMBE                      */
+    uint64_t links;            /* existing links (stored off-diagonals of a full assembly) */
 } sf3d_counters;
 uint8_t sf3d_ext_get_counters(sf3d_counters *out);
 uint8_t sf3d_ext_reset_counters(void);
@@ -244,9 +245,32 @@ uint8_t sf3d_ext_reset_counters(void);
 /* name/version of the implementation behind the ABI ("b200", "oracle", "reference") */
 const char *sf3d_ext_backend(void);
 
+/* Restore the solver parameters (types.h:291-315 defaults, deltaTcurr unset) to what a fresh
+ * process has.  The reference keeps them in a global solver object that survives
+ * cleanSF3D/initializeSF3D (cpusolver.cpp:105-134), so a second catchment in the same process
+ * would otherwise start from the previous run's deltaTcurr.  Call before sf3d_initialize. */
+uint8_t sf3d_ext_reset_solver(void);
+
 /* product only: device selection and multi-GPU slab wiring.  The other
  * two libraries return SF3D_PARAMETER_ERROR. */
 uint8_t sf3d_ext_set_device(int device);
+
+/* product only: the cudaStream_t every kernel of the library is launched on (for CUDA-event
+ * timing from the harness); NULL in the CPU libraries. */
+void *sf3d_ext_stream(void);
+
+/* product only: per-kernel device time, measured with CUDA events on the library's stream
+ * around every launch while profiling is enabled (bench.py's roofline figures). */
+enum sf3d_kernel {
+    SF3D_K_BEGIN_TRY = 0, SF3D_K_NODE_PHASE = 1, SF3D_K_ASSEMBLE = 2, SF3D_K_JACOBI = 3,
+    SF3D_K_POST = 4, SF3D_K_ACCEPT = 5, SF3D_K_OTHER = 6, SF3D_K_COUNT = 7
+};
+typedef struct sf3d_kernel_times {
+    double   ms[SF3D_K_COUNT];        /* accumulated device time per kernel kind            */
+    uint64_t launches[SF3D_K_COUNT];  /* launches per kernel kind                           */
+} sf3d_kernel_times;
+uint8_t sf3d_ext_profile(int enable);                 /* also resets the accumulators        */
+uint8_t sf3d_ext_get_kernel_times(sf3d_kernel_times *out);
 
 #ifdef __cplusplus
 }

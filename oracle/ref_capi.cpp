@@ -21,7 +21,9 @@
 
 namespace sf = soilFluxes3D::v2;
 
+#include "cpusolver.h"
 namespace soilFluxes3D::v2 {
+    extern CPUSolver CPUSolverObject;
     extern nodesData_t nodeGrid;
     extern Solver* solver;
     extern balanceData_t balanceDataCurrentTimeStep;
@@ -243,12 +245,34 @@ uint8_t sf3d_ext_get_counters(sf3d_counters *out)
     g_cnt.last_courant = sf::nodeGrid.CourantWater;
     g_cnt.last_mbr = sf::balanceDataCurrentTimeStep.waterMBR;
     g_cnt.last_mbe = sf::balanceDataCurrentTimeStep.waterMBE;
+    g_cnt.links = 0;
+    if (sf::nodeGrid.isInitialized)
+        for (int s = 0; s < SF3D_MAX_TOTAL_LINK; ++s)
+            for (uint32_t i = 0; i < sf::nodeGrid.nrNodes; ++i)
+                g_cnt.links += (sf::nodeGrid.linkData[s].linkType[i] != sf::linkType_t::NoLink);
     *out = g_cnt;
     return SF3D_OK;
 }
 uint8_t sf3d_ext_reset_counters(void) { std::memset(&g_cnt, 0, sizeof g_cnt); return SF3D_OK; }
 const char *sf3d_ext_backend(void) { return "reference"; }
 uint8_t sf3d_ext_set_device(int) { return SF3D_PARAMETER_ERROR; }
+void *sf3d_ext_stream(void) { return nullptr; }
+uint8_t sf3d_ext_profile(int) { return SF3D_PARAMETER_ERROR; }
+uint8_t sf3d_ext_get_kernel_times(sf3d_kernel_times *) { return SF3D_PARAMETER_ERROR; }
+uint8_t sf3d_ext_reset_solver(void)
+{
+    /* every field of SolverParameters back to its default (types.h:291-315); deltaTcurr = NODATA
+       makes CPUSolver::initialize pick deltaTmax again (cpusolver.cpp:30-31) */
+    const sf::SolverParameters d;
+    sf::SolverParametersPartial p;
+    p.MBRThreshold = d.MBRThreshold; p.residualTolerance = d.residualTolerance;
+    p.deltaTmin = d.deltaTmin; p.deltaTmax = d.deltaTmax; p.deltaTcurr = d.deltaTcurr;
+    p.maxApproximationsNumber = d.maxApproximationsNumber; p.maxIterationsNumber = d.maxIterationsNumber;
+    p.waterRetentionCurveModel = d.waterRetentionCurveModel; p.meanType = d.meanType;
+    p.lateralVerticalRatio = static_cast<float>(d.lateralVerticalRatio);
+    sf::CPUSolverObject.updateParameters(p);
+    return SF3D_OK;
+}
 
 /* reference-only helpers for kernel-level known-answer tests */
 void sf3d_ref_capture_jacobi(int enable) { g_capture = enable; }
