@@ -1,0 +1,256 @@
+"""Seeded scenarios shared by the CPU (oracle vs reference / golden) and GPU (product vs oracle)
+parity tests.  Each scenario drives ONE implementation of the C ABI and returns a dict of
+arrays/scalars to compare.  Edge cases follow what the reference's code paths distinguish:
+retention model and mean type, evaporation clamp, prescribed-potential / urban / road boundaries,
+saturated columns, ragged (NODATA) rasters, scalar-API graphs, empty forcing."""
+from __future__ import annotations
+
+import numpy as np
+
+from criteria3d_b200 import BoundaryType, Field, LinkType, MeanType, WRCModel
+from criteria3d_b200.synth import Catchment, run_hours, setup, _ok
+
+FIELDS = (Field.TOTAL_POTENTIAL, Field.WATER_CONTENT, Field.DEGREE_OF_SATURATION, Field.WATER_CONDUCTIVITY,
+          Field.BOUNDARY_WATER_FLOW, Field.MAX_FLOW_UP, Field.MAX_FLOW_DOWN, Field.SUM_LATERAL_FLOW)
+
+
+def snapshot(sf, n_nodes, dts, n_surface=None):
+    out = {f.name: sf.get_field(f, 0, n_nodes) for f in FIELDS}
+    out["n_surface"] = np.int64(sf.node_meta(0, n_nodes)[0].sum())
+    out["dts"] = np.asarray(dts, dtype=np.float64)
+    out["total_water"] = np.float64(sf.getTotalWaterContent())
+    out["boundary_totals"] = np.array([sf.getTotalBoundaryWaterFlow(int(b)) for b in
+                                       (BoundaryType.Runoff, BoundaryType.FreeDrainage,
+                                        BoundaryType.FreeLateralDrainage, BoundaryType.PrescribedTotalWaterPotential)])
+    c = sf.counters()
+    out["counters"] = np.array([c["approximations"], c["sweeps"]], dtype=np.float64)
+    out["mbe_mbr"] = np.array([c["last_mbe"], c["last_mbr"], c["delta_t_curr"], c["last_courant"]])
+    out["storage"] = np.float64(sf.getWaterStorage())
+    return out
+
+
+def storm(sf, shape=(24, 20, 5), hours=(20.0, 40.0), threads=1, max_steps=60, **cat_kw):
+    cat = Catchment(*shape, **cat_kw)
+    setup(sf, cat, threads=threads)
+    dts = run_hours(sf, cat, list(hours), max_steps=max_steps)
+    return snapshot(sf, cat.n_nodes, dts)
+
+
+def van_genuchten_geometric(sf, threads=1):
+    """plain VG retention, geometric mean, horizontal/vertical ratio 5, looser numerics"""
+    cat = Catchment(20, 16, 4)
+    setup(sf, cat, threads=threads, numerics=(1.0, 1800.0, 100, 8, 9, 2))
+    _ok(sf.setHydraulicProperties(int(WRCModel.VanGenuchten), int(MeanType.Geometric), 5.0), "hyd")
+    _ok(sf.set_field(Field.MATRIC_POTENTIAL, 0, cat.initial_matric_potential()), "psi")   # Se/K under the new model
+    _ok(sf.initializeBalance(), "balance")
+    dts = run_hours(sf, cat, [30.0], max_steps=40)
+    return snapshot(sf, cat.n_nodes, dts)
+
+
+def evaporation_after_rain(sf, threads=1):
+    """arithmetic mean; one wet hour, then a surface sink larger than the ponded water
+    (evaporation clamp, water.cpp:645-652)"""
+    cat = Catchment(18, 18, 4)
+    setup(sf, cat, threads=threads)
+    _ok(sf.setHydraulicProperties(int(WRCModel.ModifiedVanGenuchten), int(MeanType.Arithmetic), 10.0), "hyd")
+    dts = run_hours(sf, cat, [15.0], max_steps=40)
+    sink = np.zeros(cat.n_nodes)
+    sink[: cat.n_surface] = -cat.rain_sink_source(3.0)
+    _ok(sf.set_field(Field.WATER_SINK_SOURCE, 0, sink), "sink")
+    t = 0.0
+    while t < 1800.0 and len(dts) < 80:
+        dt = sf.computeStep(1800.0 - t)
+        dts.append(dt)
+        t += dt
+    return snapshot(sf, cat.n_nodes, dts)
+
+
+def prescribed_and_urban(sf, threads=1):
+    """bottom layer with a prescribed total potential (water table 0.5 m below the bottom nodes on
+    the left half), Urban / Road cells on layer 1, no free bottom drainage"""
+    cat = Catchment(16, 20, 4)
+    bl1 = np.zeros((cat.rows, cat.cols), np.uint8)
+    bl1[4:8, 3:9] = int(BoundaryType.Urban)
+    bl1[10:13, 10:16] = int(BoundaryType.Road)
+    cat.outlet[:] = 0
+    cat.outlet[cat.rows - 1, :] = 1
+
+    def grid_desc():
+        d = Catchment.grid_desc(cat)
+        d.boundary_l1 = bl1.ctypes.data_as(type(d.boundary_l1))
+        d.free_bottom_drainage = 0
+        return d
+    cat.grid_desc = grid_desc
+    setup(sf, cat, threads=threads)
+    last = (cat.layers - 1) * cat.n_surface
+    area = cat.cell * cat.cell
+    H0 = sf.get_field(Field.TOTAL_POTENTIAL, 0, cat.n_nodes)
+    for r in range(cat.rows):
+        for c in range(cat.cols // 2):
+            i = last + r * cat.cols + c
+            _ok(sf.setNodeBoundary(i, int(BoundaryType.PrescribedTotalWaterPotential), 0.0, area), "bc")
+            z = H0[i] - cat.initial_psi
+            _ok(sf.setNodePrescribedTotalPotential(i, z - 0.5), "presc")
+    assert sf.setNodePrescribedTotalPotential(0, 1.0) == 4          # BoundaryError on a non-prescribed node
+    _ok(sf.initializeBalance(), "balance")
+    dts = run_hours(sf, cat, [25.0], max_steps=40)
+    return snapshot(sf, cat.n_nodes, dts)
+
+
+def saturated_bottom(sf, threads=1):
+    """C4-like: lower third of the layers start saturated (psi = +0.1 m)"""
+    return storm(sf, shape=(20, 20, 9), hours=(10.0,), threads=threads, saturated_bottom=True)
+
+
+def ragged_raster(sf, threads=1):
+    """NODATA holes and a ragged edge: nodes with fewer than 8 lateral links"""
+    cat = Catchment(22, 18, 4)
+    valid = np.ones((cat.rows, cat.cols), bool)
+    valid[0:3, 0:5] = False
+    valid[9:12, 7:10] = False
+    valid[:, -1] = np.arange(cat.rows) % 3 != 0
+    rank = np.full((cat.rows, cat.cols), -1, np.int32)
+    rank[valid] = np.arange(valid.sum(), dtype=np.int32)
+    cat.cell_rank = np.ascontiguousarray(rank)
+    nv = int(valid.sum())
+    type(cat).n_surface.fget  # property stays; override sizes through a subclass-free trick below
+    cat.__class__ = type("RaggedCatchment", (Catchment,), {"n_surface": property(lambda self: nv)})
+    sink_full = cat.rain_sink_source
+
+    def rain(mm):
+        return np.ascontiguousarray(Catchment.rain_sink_source(cat, mm).reshape(cat.rows, cat.cols)[valid])
+    cat.rain_sink_source = rain
+    setup(sf, cat, threads=threads)
+    dts = run_hours(sf, cat, [30.0], max_steps=40)
+    return snapshot(sf, cat.n_nodes, dts)
+
+
+def scalar_api_column(sf, threads=1):
+    """A 3-column x 5-node graph built ONLY with the scalar API (CRITERIA-1D style), checking
+    return codes on the way; then two hours of infiltration."""
+    ncol, nlay = 3, 5
+    ns, n = ncol, ncol * nlay
+    sf.reset_solver()
+    _ok(sf.initializeSF3D(n, ns, 8, True, False, False, 0), "init")
+    _ok(sf.setSurfaceProperties(0, 0.05), "surf")
+    _ok(sf.setSoilProperties(0, 0, 3.6, 1.56, 1 - 1 / 1.56, 0.02, 0.078, 0.43, 2.9e-6, 0.5, 0.02, 0.2), "soil")
+    assert sf.setSoilProperties(0, 0, 3.6, 1.56, 1 - 1 / 1.56, 0.02, 0.078, 0.43, 2.9e-6, 0.5, 0.02, 0.2) == 6   # duplicate
+    assert sf.setSoilProperties(1, 0, -1.0, 1.56, 0.3, 0.02, 0.078, 0.43, 2.9e-6, 0.5, 0.02, 0.2) == 6           # alpha <= 0
+    thick = [0.0, 0.05, 0.10, 0.15, 0.20]
+    depth = [0.0, 0.025, 0.10, 0.225, 0.40]
+    area = 1.0
+    for lay in range(nlay):
+        for c in range(ncol):
+            i = lay * ncol + c
+            x, y, z = 1.0 * c, 0.0, 10.0 + 0.05 * c - depth[lay]
+            if lay == 0:
+                bt = int(BoundaryType.Runoff) if c == 0 else 0
+                _ok(sf.setNode(i, x, y, z, area, True, bt, 0.05, 1.0), "setNode")
+            elif lay == nlay - 1:
+                _ok(sf.setNode(i, x, y, z, area * thick[lay], False, int(BoundaryType.FreeDrainage), 0.0, area), "setNode")
+            else:
+                _ok(sf.setNode(i, x, y, z, area * thick[lay], False, 0, 0.0, 0.0), "setNode")
+    assert sf.setNode(n, 0, 0, 0, 1, True, 0, 0, 0) == 1                     # IndexError
+    for lay in range(nlay):
+        for c in range(ncol):
+            i = lay * ncol + c
+            if lay > 0:
+                _ok(sf.setNodeLink(i, i - ncol, int(LinkType.Up), area), "up")
+            if lay < nlay - 1:
+                _ok(sf.setNodeLink(i, i + ncol, int(LinkType.Down), area), "down")
+            for dc in (-1, 1):
+                if 0 <= c + dc < ncol:
+                    la = 0.5 if lay == 0 else 0.5 * thick[lay]
+                    _ok(sf.setNodeLink(i, i + dc, int(LinkType.Lateral), la), "lat")
+            if lay == 0:
+                _ok(sf.setNodeSurface(i, 0), "surface")
+                _ok(sf.setNodePond(i, 0.003), "pond")
+            else:
+                _ok(sf.setNodeSoil(i, 0, 0), "soil")
+    assert sf.setNodeLink(0, n + 3, int(LinkType.Up), 1.0) == 1              # IndexError
+    assert sf.setNodeLink(0, 1, 0, 1.0) == 6                                 # NoLink -> ParameterError
+    assert sf.setNodeSoil(0, 0, 0) == 1                                      # surface node -> IndexError
+    assert sf.setNodeSurface(ncol, 0) == 1                                   # soil node -> IndexError
+    assert sf.setNodeSoil(ncol, 7, 0) == 6                                   # unknown soil -> ParameterError
+    assert sf.setNodePond(ncol, 0.1) == 1
+    _ok(sf.setHydraulicProperties(int(WRCModel.ModifiedVanGenuchten), int(MeanType.Logarithmic), 10.0), "hyd")
+    assert sf.setHydraulicProperties(1, 2, 1000.0) == 6
+    _ok(sf.setNumericalParameters(1.0, 600.0, 100, 10, 10, 4), "num")
+    sf.setThreadsNumber(threads)
+    for i in range(n):
+        if i < ns:
+            _ok(sf.setNodeWaterContent(i, 0.001), "wc")
+        elif i < 2 * ns:
+            _ok(sf.setNodeDegreeOfSaturation(i, 0.6), "se")
+        elif i < 3 * ns:
+            _ok(sf.setNodeWaterContent(i, 0.25), "wc")
+        else:
+            _ok(sf.setNodeMatricPotential(i, -1.5), "psi")
+    assert sf.setNodeWaterContent(ncol, 1.5) == 6 and sf.setNodeDegreeOfSaturation(0, 0.5) == 1
+    _ok(sf.initializeBalance(), "balance")
+    getters = []
+    for i in (0, ncol, n - 1):
+        getters += [sf.getNodeWaterContent(i), sf.getNodeMaximumWaterContent(i), sf.getNodeMinimumWaterContent(i),
+                    sf.getNodeAvailableWaterContent(i), sf.getNodeWaterDeficit(i, 3.0), sf.getNodeDegreeOfSaturation(i),
+                    sf.getNodeWaterConductivity(i), sf.getNodeMatricPotential(i), sf.getNodeTotalPotential(i),
+                    sf.getNodePond(i), sf.getNodeBoundaryWaterFlow(i)]
+    getters += [sf.getNodeWaterContent(n + 5), sf.getNodePond(n)]                      # index sentinels
+    dts = []
+    for mm in (30.0, 0.0):
+        for c in range(ncol):
+            _ok(sf.setNodeWaterSinkSource(c, area * mm / 1000.0 / 3600.0), "sink")
+        sf.computePeriod(3600.0)
+    for i in range(2 * ncol, n):        # soil-soil links only (see compare(): stale-slot quirk Q2)
+        getters += [sf.getNodeMaxWaterFlow(i, 1), sf.getNodeMaxWaterFlow(i, 2), sf.getNodeMaxWaterFlow(i, 3),
+                    sf.getNodeSumLateralWaterFlowIn(i), sf.getNodeSumLateralWaterFlowOut(i)]
+    out = snapshot(sf, n, dts)
+    out["getters"] = np.array(getters)
+    out["water_mbr"] = np.float64(sf.getWaterMBR())
+    return out
+
+
+SCENARIOS = {
+    "storm": storm,
+    "van_genuchten_geometric": van_genuchten_geometric,
+    "evaporation_after_rain": evaporation_after_rain,
+    "prescribed_and_urban": prescribed_and_urban,
+    "saturated_bottom": saturated_bottom,
+    "ragged_raster": ragged_raster,
+    "scalar_api_column": scalar_api_column,
+}
+
+
+def compare(a: dict, b: dict, *, exact: bool, h_rel=1e-6, theta_abs=1e-7, flow_rel=1e-6, skip_stale_links=True):
+    """exact: bit-identical (oracle restatement vs reference, same libm).  Otherwise the fp64
+    tolerances stated in tests/test_gpu_parity.py."""
+    assert set(a) == set(b)
+    if exact:
+        for k in a:
+            assert np.array_equal(np.asarray(a[k]), np.asarray(b[k]), equal_nan=True), k
+        return
+    assert np.array_equal(a["dts"], b["dts"]), "accepted time-step sequence"
+    assert a["counters"][0] == b["counters"][0], "approximation count"
+    H, Hb = a["TOTAL_POTENTIAL"], b["TOTAL_POTENTIAL"]
+    assert np.max(np.abs(H - Hb) / np.maximum(1.0, np.abs(Hb))) <= h_rel
+    assert np.max(np.abs(a["WATER_CONTENT"] - b["WATER_CONTENT"])) <= theta_abs
+    assert np.max(np.abs(a["DEGREE_OF_SATURATION"] - b["DEGREE_OF_SATURATION"])) <= 1e-6
+    K, Kb = a["WATER_CONDUCTIVITY"], b["WATER_CONDUCTIVITY"]
+    assert np.all(np.abs(K - Kb) <= 1e-6 * np.abs(Kb) + 1e-18)
+    # Link flow sums: a link whose conductance was 0 at an accepted step makes the reference read a
+    # stale matrix slot (cpusolver.h:46-51); the product adds 0 for it.  Only
+    # runoff (surface-surface) and infiltration (surface-soil) conductances can be 0, so link flows
+    # are compared on soil-soil links: Up from the second soil layer on, Down and Lateral on soil nodes.
+    ns = int(b["n_surface"])
+    assert int(a["n_surface"]) == ns
+    for k, first in (("BOUNDARY_WATER_FLOW", 0), ("MAX_FLOW_UP", 2 * ns), ("MAX_FLOW_DOWN", ns), ("SUM_LATERAL_FLOW", ns)):
+        x, y = a[k][first:], b[k][first:]
+        if x.size == 0:
+            continue
+        scale = max(1e-12, float(np.max(np.abs(y))))
+        assert np.max(np.abs(x - y)) <= flow_rel * scale + 1e-12, k
+    assert a["total_water"] == np.float64(b["total_water"]) or abs(a["total_water"] - b["total_water"]) <= 1e-9 * abs(b["total_water"])
+    bt, btb = a["boundary_totals"], b["boundary_totals"]
+    assert np.all(np.abs(bt - btb) <= flow_rel * np.abs(btb) + 1e-12)
+    if "getters" in a:
+        g, gb = a["getters"], b["getters"]
+        assert np.all(np.abs(g - gb) <= 1e-6 * np.abs(gb) + 1e-12)
