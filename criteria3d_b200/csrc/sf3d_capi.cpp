@@ -64,7 +64,7 @@ struct State {
     Mirror<double> larea, lflow;
     Mirror<double> H, oldH, Se, K, sink, pond;
     // device-only
-    double *bestH = nullptr, *SeOld = nullptr, *wFlow = nullptr, *ldist = nullptr, *mval = nullptr,
+    double *bestH = nullptr, *SeOld = nullptr, *wFlow = nullptr, *lgeom = nullptr, *mval = nullptr,
            *b = nullptr, *cap = nullptr, *x0 = nullptr, *x1 = nullptr, *partA = nullptr, *partB = nullptr,
            *partC = nullptr, *scratch = nullptr;
     uint32_t *mcol = nullptr;
@@ -104,7 +104,7 @@ void fill_view()
     v.lvRatio = g_params.lateralVerticalRatio; v.heatWF = g_params.heatWeightFactor;
     v.x = S.x.d; v.y = S.y.d; v.z = S.z.d; v.size = S.size.d; v.meta = S.meta.d; v.tab = S.tab.d;
     v.bSlope = S.bSlope.d; v.bSize = S.bSize.d; v.bRate = S.bRate.d; v.bSum = S.bSum.d; v.bPresc = S.bPresc.d;
-    v.lidx = S.lidx.d; v.larea = S.larea.d; v.lflow = S.lflow.d; v.ldist = S.ldist;
+    v.lidx = S.lidx.d; v.larea = S.larea.d; v.lflow = S.lflow.d; v.lgeom = S.lgeom;
     v.H = S.H.d; v.oldH = S.oldH.d; v.bestH = S.bestH; v.Se = S.Se.d; v.SeOld = S.SeOld; v.K = S.K.d;
     v.wFlow = S.wFlow; v.sink = S.sink.d; v.pond = S.pond.d; v.inv = nullptr;
     v.mcol = S.mcol; v.mval = S.mval; v.b = S.b; v.cap = S.cap; v.x0 = S.x0; v.x1 = S.x1;
@@ -213,7 +213,7 @@ void release_all()
     S.bRate.release(); S.bSum.release(); S.bPresc.release(); S.meta.release(); S.lidx.release();
     S.culvertOf.release(); S.tab.release(); S.larea.release(); S.lflow.release();
     S.H.release(); S.oldH.release(); S.Se.release(); S.K.release(); S.sink.release(); S.pond.release();
-    double **devOnly[] = {&S.bestH, &S.SeOld, &S.wFlow, &S.ldist, &S.mval, &S.b, &S.cap, &S.x0, &S.x1,
+    double **devOnly[] = {&S.bestH, &S.SeOld, &S.wFlow, &S.lgeom, &S.mval, &S.b, &S.cap, &S.x0, &S.x1,
                           &S.partA, &S.partB, &S.partC, &S.scratch};
     for (double **p : devOnly) { dev_free(*p); *p = nullptr; }
     dev_free(S.mcol); S.mcol = nullptr;
@@ -256,7 +256,7 @@ uint8_t sf3d_initialize(uint32_t nrNodes, uint32_t nrSurfaceNodes, uint8_t nrLat
         S.H.alloc(N); S.oldH.alloc(N); S.Se.alloc(N); S.K.alloc(N); S.sink.alloc(N); S.pond.alloc(nrSurfaceNodes);
         S.culvertOf.alloc(nrSurfaceNodes);
         S.bestH = (double *)dev_alloc(N * 8); S.SeOld = (double *)dev_alloc(N * 8); S.wFlow = (double *)dev_alloc(N * 8);
-        S.ldist = (double *)dev_alloc(L * 8); S.mval = (double *)dev_alloc(L * 8); S.mcol = (uint32_t *)dev_alloc(L * 4);
+        S.lgeom = (double *)dev_alloc(L * 8); S.mval = (double *)dev_alloc(L * 8); S.mcol = (uint32_t *)dev_alloc(L * 4);
         S.b = (double *)dev_alloc(N * 8); S.cap = (double *)dev_alloc(N * 8);
         S.x0 = (double *)dev_alloc(N * 8); S.x1 = (double *)dev_alloc(N * 8);
         const size_t nb = (size_t)reduce_blocks(0xFFFFFFFFu);
@@ -393,6 +393,7 @@ uint8_t sf3d_set_hydraulic_properties(uint8_t wrc, uint8_t meanType, float ratio
     g_params.wrcModel = wrc;
     g_params.meanType = meanType;
     g_params.lateralVerticalRatio = ratio;       // float -> double, as SolverParametersPartial does
+    S.topoDirty = true;                          // the static link factors fold the ratio in
     return SF3D_OK;
 }
 

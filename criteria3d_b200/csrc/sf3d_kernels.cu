@@ -217,14 +217,14 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_link_geometry(SF3DView v, int
         {
             const int slot = sf3d_slot_of_col(c);
             uint32_t j = i;
-            double d = 0.;
+            double g = 0.;
             if (META_HAS_SLOT(m, slot))
             {
                 j = v.lidx[(size_t)slot * N + i];
-                d = sf3d_link_distance(v, i, j, slot);
+                g = sf3d_link_geom(v, i, j, slot, v.larea[(size_t)slot * N + i]);
             }
             v.mcol[(size_t)c * N + i] = j;
-            v.ldist[(size_t)slot * N + i] = d;
+            v.lgeom[(size_t)c * N + i] = g;
         }
     }
 }

@@ -72,6 +72,9 @@ SF3D_HD double sf3d_mualem(const SoilRec &s, int model, double Se)
     }
     else
         return SF3D_NODATA;
+#ifndef SF3D_REFERENCE_ROUNDING
+    if (s.L == 0.5) return s.Ksat * sqrt(Se) * (temp * temp);      // Mualem's L = 0.5: exact square root
+#endif
     return s.Ksat * pow(Se, s.L) * (temp * temp);
 }
 
@@ -276,13 +279,24 @@ SF3D_HD void sf3d_row_node_phase(const SF3DView &v, uint32_t i, double dt, int w
 // link conductances: Water::computeLinkFluxes dispatch (water.cpp:300-343)
 // ==========================================================================================
 
-// Water::redistribution (water.cpp:542-562); dist = 3-D distance (lateral) or |dz| (vertical)
-SF3D_HD double sf3d_redistribution(const SF3DView &v, uint32_t i, uint32_t j, int slot, double area, double dist)
+// Water::redistribution (water.cpp:542-562).
+// Reference: cellDistance = 3-D distance (lateral) or |dz| (vertical); lateral K scaled by the
+// horizontal/vertical ratio; (mean(Ki,Kj) * area) / distance.
+// Product build: the static factor geom = area / distance (x ratio for lateral links; every mean is
+// homogeneous of degree 1) is precomputed per link by kern_link_geometry, which removes one fp64
+// division, two multiplications and one 8-byte load per link; the result differs from the
+// reference expression by rounding only (<= 2 ulp).  -DSF3D_REFERENCE_ROUNDING keeps the
+// reference's exact expression (geom then holds the distance).
+SF3D_HD double sf3d_redistribution(const SF3DView &v, double ki, double kj, int slot, double area, double geom)
 {
-    double ki = v.K[i], kj = v.K[j];
+#ifdef SF3D_REFERENCE_ROUNDING
+    if (geom == 0.) return 0.;
     if (slot >= 2) { ki *= v.lvRatio; kj *= v.lvRatio; }
-    const double meanK = sf3d_mean(ki, kj, v.meanType);
-    return (meanK * area) / dist;
+    return (sf3d_mean(ki, kj, v.meanType) * area) / geom;
+#else
+    (void)slot; (void)area;
+    return sf3d_mean(ki, kj, v.meanType) * geom;
+#endif
 }
 
 // Water::infiltration (water.cpp:490-539); dist = z[surface] - z[soil]
@@ -353,17 +367,67 @@ SF3D_HD double sf3d_heat_thermal_invariant(const SF3DView &v, uint32_t i, int sl
 // ==========================================================================================
 // assembly of one row: CPUSolver::computeLinearSystemElement + computeDiagonalElement +
 // preconditioningMatrix (cpusolver.cpp:348-389, 335-345, 284-305).  Returns the row's Courant.
+// Columns are visited in the reference's order (Up, Lateral 0..7, Down).  v.mcol[c] is the linked
+// node of column c, or the row itself when the link does not exist (then geom = 0).
 // ==========================================================================================
-SF3D_HD double sf3d_row_assemble(const SF3DView &v, uint32_t i, double dt, int approx)
+SF3D_HD void sf3d_row_store(const SF3DView &v, uint32_t i, double dt, const double *k, double sum, double invariant)
+{
+    const size_t N = v.N;
+    const double capOverDt = v.cap[i] / dt;
+    const double diag = capOverDt + sum;              // cpusolver.cpp:344
+    const double invDiag = 1.0 / diag;                // cpusolver.cpp:291
+    #pragma unroll
+    for (int c = 0; c < SF3D_NLINK; ++c)
+        v.mval[(size_t)c * N + i] = (-k[c]) * invDiag;     // cpusolver.cpp:380-383, 294-297
+    const double rhs = (capOverDt * v.oldH[i]) + v.wFlow[i] + invariant;   // :387-388 (invariant = 0 without heat)
+    v.b[i] = rhs * invDiag;                           // cpusolver.cpp:300
+}
+
+// soil row: every link is a redistribution except an Up link to a surface node (infiltration).
+// The ten neighbour conductivities are gathered first (independent loads), then the means.
+SF3D_HD double sf3d_row_assemble_soil(const SF3DView &v, uint32_t i, double dt)
+{
+    const size_t N = v.N;
+    const double ki = v.K[i];
+    uint32_t j[SF3D_NLINK];
+    double g[SF3D_NLINK], kj[SF3D_NLINK], k[SF3D_NLINK];
+    #pragma unroll
+    for (int c = 0; c < SF3D_NLINK; ++c) { j[c] = v.mcol[(size_t)c * N + i]; g[c] = v.lgeom[(size_t)c * N + i]; }
+    #pragma unroll
+    for (int c = 0; c < SF3D_NLINK; ++c) kj[c] = v.K[j[c]];
+
+    double sum = 0., invariant = 0.;
+    #pragma unroll
+    for (int c = 0; c < SF3D_NLINK; ++c)
+    {
+        const int slot = sf3d_slot_of_col(c);
+        double kc;
+        if (c == 0 && j[0] < v.Ns)                    // first soil layer: link to the surface node above
+            kc = sf3d_infiltration(v, j[0], i, dt, v.larea[i], g[0]);
+        else
+        {
+#ifdef SF3D_REFERENCE_ROUNDING
+            const double area = v.larea[(size_t)slot * N + i];
+#else
+            const double area = 0.;
+#endif
+            kc = sf3d_redistribution(v, ki, kj[c], slot, area, g[c]);
+            if (v.computeHeat && j[c] != i) invariant += sf3d_heat_thermal_invariant(v, i, slot, j[c]);
+        }
+        k[c] = kc;
+        sum += kc;                                    // zero entries are not stored in the reference; +0 is exact
+    }
+    sf3d_row_store(v, i, dt, k, sum, invariant);
+    return 0.;
+}
+
+// surface row: runoff links to surface neighbours, infiltration link to the soil node below
+SF3D_HD double sf3d_row_assemble_surface(const SF3DView &v, uint32_t i, double dt, int approx)
 {
     const size_t N = v.N;
     const uint32_t m = v.meta[i];
-    const bool iSurface = META_SURFACE(m);
     double k[SF3D_NLINK];
-    double sum = 0.;
-    double courant = 0.;
-    double invariant = 0.;            // invariantFluxes of this row (heat-coupled runs only)
-
+    double sum = 0., courant = 0.;
     #pragma unroll
     for (int c = 0; c < SF3D_NLINK; ++c)
     {
@@ -371,35 +435,22 @@ SF3D_HD double sf3d_row_assemble(const SF3DView &v, uint32_t i, double dt, int a
         double kc = 0.;
         if (META_HAS_SLOT(m, slot))
         {
-            const size_t li = (size_t)slot * N + i;
-            const uint32_t j = v.lidx[li];
-            const double area = v.larea[li];
-            const double dist = v.ldist[li];
-            const bool jSurface = j < v.Ns;          // surface nodes are [0, Ns) (checked at finalize)
-            if (!iSurface && !jSurface)
-            {
-                kc = sf3d_redistribution(v, i, j, slot, area, dist);
-                if (v.computeHeat) invariant += sf3d_heat_thermal_invariant(v, i, slot, j);
-            }
-            else if (iSurface && jSurface)
-                kc = sf3d_runoff(v, i, j, approx, dt, area, dist, &courant);
-            else
-                kc = iSurface ? sf3d_infiltration(v, i, j, dt, area, dist)
-                              : sf3d_infiltration(v, j, i, dt, area, dist);
+            const uint32_t j = v.mcol[(size_t)c * N + i];
+            const double area = v.larea[(size_t)slot * N + i];
+            const double dist = v.lgeom[(size_t)c * N + i];
+            if (j < v.Ns) kc = sf3d_runoff(v, i, j, approx, dt, area, dist, &courant);
+            else          kc = sf3d_infiltration(v, i, j, dt, area, dist);
         }
         k[c] = kc;
-        sum += kc;                                    // zero entries are not stored in the reference; +0 is exact
+        sum += kc;
     }
-
-    const double capOverDt = v.cap[i] / dt;
-    const double diag = capOverDt + sum;              // cpusolver.cpp:344
-    const double invDiag = 1.0 / diag;                // cpusolver.cpp:291
-    #pragma unroll
-    for (int c = 0; c < SF3D_NLINK; ++c)
-        v.mval[(size_t)c * N + i] = (-k[c]) * invDiag;     // cpusolver.cpp:380-383, 294-297
-    const double rhs = (capOverDt * v.oldH[i]) + v.wFlow[i] + (v.computeHeat ? invariant : 0.);   // :387-388
-    v.b[i] = rhs * invDiag;                           // cpusolver.cpp:300
+    sf3d_row_store(v, i, dt, k, sum, 0.);
     return courant;
+}
+
+SF3D_HD double sf3d_row_assemble(const SF3DView &v, uint32_t i, double dt, int approx)
+{
+    return (i < v.Ns) ? sf3d_row_assemble_surface(v, i, dt, approx) : sf3d_row_assemble_soil(v, i, dt);
 }
 
 // ==========================================================================================
@@ -498,7 +549,7 @@ SF3D_HD void sf3d_row_restore_best(const SF3DView &v, uint32_t i)
 // ==========================================================================================
 SF3D_HD double sf3d_link_distance(const SF3DView &v, uint32_t i, uint32_t j, int slot)
 {
-    const bool iS = META_SURFACE(v.meta[i]), jS = META_SURFACE(v.meta[j]);
+    const bool iS = i < v.Ns, jS = j < v.Ns;
     const double dx = v.x[i] - v.x[j], dy = v.y[i] - v.y[j], dz = v.z[i] - v.z[j];
     if (!iS && !jS)
     {
@@ -507,4 +558,21 @@ SF3D_HD double sf3d_link_distance(const SF3DView &v, uint32_t i, uint32_t j, int
     }
     if (iS && jS) { double n = 0; n += dx * dx; n += dy * dy; return sqrt(n); }
     return iS ? dz : -dz;           // z[surface] - z[soil]
+}
+
+// what v.lgeom holds for link (i -> j): the distance, except soil-soil links of the product build,
+// which hold area / distance (x horizontal/vertical ratio for lateral links); see sf3d_redistribution
+SF3D_HD double sf3d_link_geom(const SF3DView &v, uint32_t i, uint32_t j, int slot, double area)
+{
+    const double d = sf3d_link_distance(v, i, j, slot);
+#ifndef SF3D_REFERENCE_ROUNDING
+    if (i >= v.Ns && j >= v.Ns)
+    {
+        const double g = area / d;
+        return (slot >= 2) ? g * v.lvRatio : g;
+    }
+#else
+    (void)area;
+#endif
+    return d;
 }

@@ -91,7 +91,7 @@ struct SF3DView {
     // links, slot-major: [slot*N + i]
     uint32_t *lidx;
     double *larea, *lflow;
-    double *ldist;                  // static link geometry (see k_link_geometry)
+    double *lgeom;                  // static link geometry, COLUMN-major (see sf3d_link_geom)
     // water state
     double *H, *oldH, *bestH, *Se, *SeOld, *K, *wFlow, *sink, *pond, *inv;
     // linear system, COLUMN-major: [col*N + i]; mcol is static
