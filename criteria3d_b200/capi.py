@@ -243,6 +243,11 @@ _EXT = [
     ("sf3d_ext_backend", C.c_char_p, []),
     ("sf3d_ext_set_device", u8, [cint]),
     ("sf3d_ext_reset_solver", u8, []),
+    ("sf3d_ext_comm_unique_id", u8, [C.POINTER(u8)]),
+    ("sf3d_ext_comm_init", u8, [cint, cint, C.POINTER(u8)]),
+    ("sf3d_ext_comm_finalize", u8, []),
+    ("sf3d_ext_set_halo", u8, [u32, C.POINTER(C.c_int32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32),
+                               C.POINTER(u32), C.c_uint64]),
     ("sf3d_ext_stream", C.c_void_p, []),
     ("sf3d_ext_profile", u8, [cint]),
     ("sf3d_ext_get_kernel_times", u8, [C.POINTER(KernelTimes)]),
@@ -321,6 +326,30 @@ class SoilFluxes3D:
 
     def set_device(self, device: int) -> int:
         return self.lib.sf3d_ext_set_device(device)
+
+    # ---- multi-GPU slabs (product only) -----------------------------------------
+    def comm_unique_id(self) -> bytes:
+        buf = (u8 * 128)()
+        rc = self.lib.sf3d_ext_comm_unique_id(buf)
+        if rc:
+            raise RuntimeError(f"sf3d_ext_comm_unique_id -> {SF3Derror(rc).name}")
+        return bytes(buf)
+
+    def comm_init(self, rank: int, world: int, uid: bytes) -> int:
+        buf = (u8 * 128).from_buffer_copy(uid)
+        return self.lib.sf3d_ext_comm_init(rank, world, buf)
+
+    def comm_finalize(self) -> int:
+        return self.lib.sf3d_ext_comm_finalize()
+
+    def set_halo(self, peers, send_lists, recv_lists, n_global_nodes: int) -> int:
+        peers_a = np.ascontiguousarray(peers, dtype=np.int32)
+        sc = np.ascontiguousarray([len(x) for x in send_lists], dtype=np.uint32)
+        rc_ = np.ascontiguousarray([len(x) for x in recv_lists], dtype=np.uint32)
+        si = np.ascontiguousarray(np.concatenate(send_lists) if len(send_lists) else np.zeros(0), dtype=np.uint32)
+        ri = np.ascontiguousarray(np.concatenate(recv_lists) if len(recv_lists) else np.zeros(0), dtype=np.uint32)
+        return self.lib.sf3d_ext_set_halo(len(peers_a), _ptr(peers_a, C.c_int32), _ptr(sc, u32), _ptr(si, u32),
+                                          _ptr(rc_, u32), _ptr(ri, u32), int(n_global_nodes))
 
     def reset_solver(self) -> int:
         return self.lib.sf3d_ext_reset_solver()

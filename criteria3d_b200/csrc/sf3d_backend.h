@@ -30,6 +30,17 @@ void   prof_enable(bool on);             // CUDA-event timing of every launch, p
 void   prof_get(double ms[SF3D_K_COUNT], uint64_t n[SF3D_K_COUNT]);
 uint64_t k_count_links(const SF3DView &v);
 
+// ---- row-slab ranks (NCCL resolved at run time; see sf3d_kernels.cu) ------------------------
+void comm_unique_id(unsigned char out[128]);
+void comm_init(int rank, int world, const unsigned char id[128]);
+void comm_finalize();
+int  comm_world();
+int  comm_rank();
+void comm_clear_halo();
+void comm_add_halo_peer(int peer, uint32_t nSend, const uint32_t *sendIdx, uint32_t nRecv, const uint32_t *recvIdx);
+void comm_allreduce(double *devValues, int count, bool isMax);
+void comm_halo(double *x);
+
 // ---- kernels -----------------------------------------------------------------------------
 int  reduce_blocks(uint32_t n);          // grid size used by all reducing kernels for n rows
 void k_link_geometry(const SF3DView &v, int *surfaceOrderOk);

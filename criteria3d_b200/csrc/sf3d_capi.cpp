@@ -48,6 +48,7 @@ struct State {
     bool water = true, heat = false, solutes = false, heatVapor = false, heatAdvection = false;
     uint8_t hfMode = 0;
     uint32_t N = 0, Ns = 0;
+    double nGlobal = 0.;                 // owned nodes over all ranks (multi-GPU slabs)
 
     std::vector<SoilRec> soils;
     std::vector<std::pair<uint16_t, uint8_t>> soilKeys;   // (soilNumber, horizonNumber) of each record
@@ -98,6 +99,8 @@ void fill_view()
     SF3DView &v = S.eng.v;
     memset(&v, 0, sizeof v);
     v.N = S.N; v.Ns = S.Ns;
+    v.world = (uint32_t)comm_world();
+    v.nGlobal = (v.world > 1 && S.nGlobal > 0.) ? S.nGlobal : (double)S.N;
     v.computeHeat = S.heat; v.computeHeatVapor = S.heatVapor; v.computeHeatAdvection = S.heatAdvection;
     v.hfSaveMode = S.hfMode;
     v.wrcModel = g_params.wrcModel; v.meanType = g_params.meanType;
@@ -246,7 +249,8 @@ uint8_t sf3d_initialize(uint32_t nrNodes, uint32_t nrSurfaceNodes, uint8_t nrLat
         S.water = isComputeWater != 0; S.heat = isComputeHeat != 0; S.solutes = isComputeSolutes != 0;
         S.heatVapor = S.heatAdvection = false; S.hfMode = 0;
         if (S.heat) { S.heatVapor = true; S.heatAdvection = true; S.hfMode = hfMode; }
-        S.N = nrNodes; S.Ns = nrSurfaceNodes;
+        S.N = nrNodes; S.Ns = nrSurfaceNodes; S.nGlobal = 0.;
+        comm_clear_halo();
         if (nrLateralLinks > SF3D_MAX_LATERAL_LINK) return SF3D_PARAMETER_ERROR;
 
         const size_t N = nrNodes, L = (size_t)SF3D_NLINK * N;
@@ -938,6 +942,41 @@ uint8_t sf3d_ext_set_device(int device)
 }
 
 uint8_t sf3d_ext_reset_solver(void) { g_params = default_params(); return SF3D_OK; }
+
+uint8_t sf3d_ext_comm_unique_id(uint8_t id[128])
+{ return guarded([&]() -> uint8_t { dev_select(g_device); comm_unique_id(id); return SF3D_OK; }, (uint8_t)SF3D_SOLVER_ERROR); }
+uint8_t sf3d_ext_comm_init(int rank, int world, const uint8_t id[128])
+{
+    if (S.initialized) return SF3D_PARAMETER_ERROR;     // wire the ranks before initializeSF3D
+    return guarded([&]() -> uint8_t { dev_select(g_device); comm_init(rank, world, id); return SF3D_OK; }, (uint8_t)SF3D_SOLVER_ERROR);
+}
+uint8_t sf3d_ext_comm_finalize(void)
+{ return guarded([&]() -> uint8_t { comm_finalize(); return SF3D_OK; }, (uint8_t)SF3D_SOLVER_ERROR); }
+uint8_t sf3d_ext_set_halo(uint32_t nPeers, const int32_t *peers, const uint32_t *sendCount, const uint32_t *sendIdx,
+                          const uint32_t *recvCount, const uint32_t *recvIdx, uint64_t nGlobalNodes)
+{
+    return guarded([&]() -> uint8_t {
+        REQUIRE_INIT_E();
+        if (nPeers && (!peers || !sendCount || !recvCount)) return SF3D_PARAMETER_ERROR;
+        comm_clear_halo();
+        uint32_t *meta = S.meta.rw();
+        for (uint32_t i = 0; i < S.N; ++i) meta[i] &= ~(1u << 19);
+        size_t so = 0, ro = 0;
+        for (uint32_t p = 0; p < nPeers; ++p)
+        {
+            for (uint32_t k = 0; k < sendCount[p]; ++k) if (sendIdx[so + k] >= S.N) return SF3D_INDEX_ERROR;
+            for (uint32_t k = 0; k < recvCount[p]; ++k)
+            {
+                if (recvIdx[ro + k] >= S.N) return SF3D_INDEX_ERROR;
+                meta[recvIdx[ro + k]] |= (1u << 19);               // ghost
+            }
+            comm_add_halo_peer(peers[p], sendCount[p], sendIdx + so, recvCount[p], recvIdx + ro);
+            so += sendCount[p]; ro += recvCount[p];
+        }
+        S.nGlobal = (double)nGlobalNodes;
+        return SF3D_OK;
+    }, (uint8_t)SF3D_SOLVER_ERROR);
+}
 void *sf3d_ext_stream(void) { return guarded([&]() -> void * { return dev_stream(); }, (void *)nullptr); }
 uint8_t sf3d_ext_profile(int enable)
 { return guarded([&]() -> uint8_t { prof_enable(enable != 0); return SF3D_OK; }, (uint8_t)SF3D_SOLVER_ERROR); }

@@ -15,6 +15,7 @@
 //     batch of sweeps can be enqueued without synchronising; sweeps launched after convergence
 //     return immediately.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -247,15 +248,49 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_node_phase(SF3DView v, double
         sf3d_row_node_phase(v, i, dt, withCapacity);
 }
 
+// the stopping / Courant rules, applied either by the last block of the producing kernel (single
+// GPU) or by a one-thread kernel after the all-reduce of the local values (row-slab ranks)
+__device__ __forceinline__ void rule_courant(Ctrl *c, double cmax, double dt, double dtMin)
+{
+    c->courantMax = cmax;
+    const bool ok = (cmax < 1.01) || (dt <= dtMin);      // CPUSolver::checkCourant, cpusolver.cpp:259
+    c->status = ok ? SOLVE_RUNNING : SOLVE_COURANT_FAIL;
+    c->sweeps = 0;
+    c->bestNorm = 1.;       // solveLinearSystem: bestErrorNorm = 1 (cpusolver.cpp:674)
+    c->lastNorm = 0.;
+}
+__device__ __forceinline__ void rule_jacobi(Ctrl *c, double total, double nGlobal, int maxIter, double tol)
+{
+    const double curr = total / nGlobal;                      // water.cpp:600
+    c->lastNorm = curr;
+    c->sweeps += 1;
+    if (curr < tol) c->status = SOLVE_CONVERGED;              // cpusolver.cpp:692
+    else if (curr > c->bestNorm * 10) c->status = SOLVE_DIVERGED;   // :695
+    else
+    {
+        if (curr < c->bestNorm) c->bestNorm = curr;           // :698
+        if (c->sweeps >= maxIter) c->status = SOLVE_MAXITER;
+    }
+}
+__global__ void kern_rule_courant(Ctrl *c, double dt, double dtMin) { rule_courant(c, c->red[0], dt, dtMin); }
+__global__ void kern_rule_jacobi(Ctrl *c, double nGlobal, int maxIter, double tol)
+{
+    if (c->status != SOLVE_RUNNING) return;
+    rule_jacobi(c, c->red[0], nGlobal, maxIter, tol);
+}
+__global__ void kern_rule_post(Ctrl *c) { c->storage = c->red[0]; c->sinkSum = c->red[1]; }
+__global__ void kern_rule_boundary(Ctrl *c) { c->boundarySum = c->red[0]; }
+
 // link phase: conductances, diagonal, row normalisation, right-hand side, per-row Courant;
 // the last block publishes max Courant and arms the on-device solver state
-// (CPUSolver::checkCourant test, cpusolver.cpp:248-260)
+// (CPUSolver::checkCourant test, cpusolver.cpp:248-260).  Ghost rows are not assembled.
 __global__ void __launch_bounds__(SF3D_BLOCK) kern_assemble(SF3DView v, double dt, int approx, double dtMin)
 {
     __shared__ double sh[SF3D_BLOCK / 32];
     double courant = 0.;
     for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
     {
+        if (v.world > 1 && META_GHOST(v.meta[i])) continue;
         const double c = sf3d_row_assemble(v, i, dt, approx);
         courant = (courant < c) ? c : courant;
     }
@@ -266,20 +301,15 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_assemble(SF3DView v, double d
         const double cmax = fold_partials<true>(v.partA, sh);
         if (threadIdx.x == 0)
         {
-            Ctrl *c = v.ctrl;
-            c->courantMax = cmax;
-            const bool ok = (cmax < 1.01) || (dt <= dtMin);
-            c->status = ok ? SOLVE_RUNNING : SOLVE_COURANT_FAIL;
-            c->sweeps = 0;
-            c->bestNorm = 1.;       // solveLinearSystem: bestErrorNorm = 1 (cpusolver.cpp:674)
-            c->lastNorm = 0.;
-            c->ticket = 0;
+            if (v.world == 1) rule_courant(v.ctrl, cmax, dt, dtMin);
+            else v.ctrl->red[0] = cmax;
+            v.ctrl->ticket = 0;
         }
     }
 }
 
 // one Jacobi sweep (Water::JacobiWaterCPU) + the stopping rule of CPUSolver::solveLinearSystem
-// (cpusolver.cpp:678-700) evaluated by the last block
+// (cpusolver.cpp:678-700) evaluated by the last block.  Ghost rows are filled by the halo exchange.
 __global__ void __launch_bounds__(SF3D_BLOCK) kern_jacobi(SF3DView v, const double *__restrict__ xin,
                                                           double *__restrict__ xout, int maxIter, double tol)
 {
@@ -287,7 +317,10 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_jacobi(SF3DView v, const doub
     __shared__ double sh[SF3D_BLOCK / 32];
     double norm = 0.;
     for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
+    {
+        if (v.world > 1 && META_GHOST(v.meta[i])) continue;
         norm += sf3d_row_jacobi(v, i, xin, xout);
+    }
     norm = block_reduce<false>(norm, sh);
     if (threadIdx.x == 0) v.partA[blockIdx.x] = norm;
     if (last_block(v.ctrl))
@@ -295,20 +328,23 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_jacobi(SF3DView v, const doub
         const double total = fold_partials<false>(v.partA, sh);
         if (threadIdx.x == 0)
         {
-            Ctrl *c = v.ctrl;
-            const double curr = total / v.N;                      // water.cpp:600
-            c->lastNorm = curr;
-            c->sweeps += 1;
-            if (curr < tol) c->status = SOLVE_CONVERGED;          // cpusolver.cpp:692
-            else if (curr > c->bestNorm * 10) c->status = SOLVE_DIVERGED;   // :695
-            else
-            {
-                if (curr < c->bestNorm) c->bestNorm = curr;       // :698
-                if (c->sweeps >= maxIter) c->status = SOLVE_MAXITER;
-            }
-            c->ticket = 0;
+            if (v.world == 1) rule_jacobi(v.ctrl, total, v.nGlobal, maxIter, tol);
+            else v.ctrl->red[0] = total;
+            v.ctrl->ticket = 0;
         }
     }
+}
+
+// halo exchange helpers: gather owned boundary values into a send buffer / scatter received ones
+__global__ void __launch_bounds__(SF3D_BLOCK) kern_pack(const double *__restrict__ x, const uint32_t *__restrict__ idx,
+                                                        uint32_t n, double *__restrict__ buf)
+{
+    for (uint32_t k = blockIdx.x * SF3D_BLOCK + threadIdx.x; k < n; k += gridDim.x * SF3D_BLOCK) buf[k] = x[idx[k]];
+}
+__global__ void __launch_bounds__(SF3D_BLOCK) kern_unpack(double *__restrict__ x, const uint32_t *__restrict__ idx,
+                                                          uint32_t n, const double *__restrict__ buf)
+{
+    for (uint32_t k = blockIdx.x * SF3D_BLOCK + threadIdx.x; k < n; k += gridDim.x * SF3D_BLOCK) x[idx[k]] = buf[k];
 }
 
 // H = x, Se refresh, and the two mass-balance sums
@@ -320,6 +356,7 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_post(SF3DView v, const double
     {
         double s, q;
         sf3d_row_post(v, i, x, dt, mode, &s, &q);
+        if (v.world > 1 && META_GHOST(v.meta[i])) continue;      // ghosts are counted by their owner
         storage += s;
         sinkSum += q;
     }
@@ -330,14 +367,19 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_post(SF3DView v, const double
     {
         const double st = fold_partials<false>(v.partA, sh);
         const double sk = fold_partials<false>(v.partB, sh);
-        if (threadIdx.x == 0) { v.ctrl->storage = st; v.ctrl->sinkSum = sk; v.ctrl->ticket = 0; }
+        if (threadIdx.x == 0)
+        {
+            if (v.world == 1) { v.ctrl->storage = st; v.ctrl->sinkSum = sk; }
+            else { v.ctrl->red[0] = st; v.ctrl->red[1] = sk; }
+            v.ctrl->ticket = 0;
+        }
     }
 }
 
 __global__ void __launch_bounds__(SF3D_BLOCK) kern_accept(SF3DView v, double dt)
 {
     for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
-        sf3d_row_accept(v, i, dt);
+        if (!(v.world > 1 && META_GHOST(v.meta[i]))) sf3d_row_accept(v, i, dt);
 }
 
 __global__ void __launch_bounds__(SF3D_BLOCK) kern_restore_best(SF3DView v)
@@ -352,13 +394,17 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_total_boundary(SF3DView v, ui
     __shared__ double sh[SF3D_BLOCK / 32];
     double sum = 0.;
     for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
-        if (META_BT(v.meta[i]) == bt) sum += v.bSum[i];
+        if (META_BT(v.meta[i]) == bt && !(v.world > 1 && META_GHOST(v.meta[i]))) sum += v.bSum[i];
     sum = block_reduce<false>(sum, sh);
     if (threadIdx.x == 0) v.partA[blockIdx.x] = sum;
     if (last_block(v.ctrl))
     {
         const double t = fold_partials<false>(v.partA, sh);
-        if (threadIdx.x == 0) { v.ctrl->boundarySum = t; v.ctrl->ticket = 0; }
+        if (threadIdx.x == 0)
+        {
+            if (v.world == 1) v.ctrl->boundarySum = t; else v.ctrl->red[0] = t;
+            v.ctrl->ticket = 0;
+        }
     }
 }
 
@@ -547,6 +593,119 @@ __global__ void kern_fill(double *p, size_t n, double value)
 }
 
 // ------------------------------------------------------------------------------------------
+// row-slab ranks: NCCL over NVLink for the per-sweep halo of x and the scalar all-reduces.
+// libnccl is resolved at run time (dlopen) so that single-GPU users need only libcudart; the
+// few entry points used are declared here with the signatures of nccl.h (2.x ABI).
+// ------------------------------------------------------------------------------------------
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { NCCL_SUM = 0, NCCL_MAX = 2, NCCL_FLOAT64 = 8 };
+static struct {
+    void *lib = nullptr;
+    int (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+} nccl;
+static ncclComm_t g_comm = nullptr;
+static int g_rank = 0, g_world = 1;
+struct HaloPeer { int peer; uint32_t nSend, nRecv; uint32_t *sendIdx, *recvIdx; double *sendBuf, *recvBuf; };
+static std::vector<HaloPeer> g_halo;
+
+#define NCCL_OK(call)                                                                          \
+    do {                                                                                       \
+        int r_ = (call);                                                                       \
+        if (r_ != 0) {                                                                         \
+            fprintf(stderr, "[sf3d_b200] NCCL error %d (%s) at %s:%d: %s\n", r_,               \
+                    nccl.GetErrorString ? nccl.GetErrorString(r_) : "?", __FILE__, __LINE__, #call); \
+            throw DeviceError{r_, "NCCL", #call};                                              \
+        }                                                                                      \
+    } while (0)
+
+static void nccl_load()
+{
+    if (nccl.lib) return;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) { nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (nccl.lib) break; }
+    if (!nccl.lib) throw DeviceError{-1, "libnccl.so.2 not found", "dlopen"};
+    auto sym = [&](const char *n) { void *p = dlsym(nccl.lib, n); if (!p) throw DeviceError{-1, "NCCL symbol missing", n}; return p; };
+    nccl.GetUniqueId = (int (*)(ncclUniqueId *))sym("ncclGetUniqueId");
+    nccl.CommInitRank = (int (*)(ncclComm_t *, int, ncclUniqueId, int))sym("ncclCommInitRank");
+    nccl.CommDestroy = (int (*)(ncclComm_t))sym("ncclCommDestroy");
+    nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t))sym("ncclAllReduce");
+    nccl.Send = (int (*)(const void *, size_t, int, int, ncclComm_t, cudaStream_t))sym("ncclSend");
+    nccl.Recv = (int (*)(void *, size_t, int, int, ncclComm_t, cudaStream_t))sym("ncclRecv");
+    nccl.GroupStart = (int (*)())sym("ncclGroupStart");
+    nccl.GroupEnd = (int (*)())sym("ncclGroupEnd");
+    nccl.GetErrorString = (const char *(*)(int))sym("ncclGetErrorString");
+}
+void comm_unique_id(unsigned char out[128])
+{
+    nccl_load();
+    ncclUniqueId id;
+    NCCL_OK(nccl.GetUniqueId(&id));
+    memcpy(out, id.internal, 128);
+}
+void comm_init(int rank, int world, const unsigned char idBytes[128])
+{
+    ensure_device();
+    nccl_load();
+    if (g_comm) { nccl.CommDestroy(g_comm); g_comm = nullptr; }
+    ncclUniqueId id;
+    memcpy(id.internal, idBytes, 128);
+    NCCL_OK(nccl.CommInitRank(&g_comm, world, id, rank));
+    g_rank = rank; g_world = world;
+}
+int comm_world() { return g_world; }
+int comm_rank() { return g_rank; }
+void comm_clear_halo()
+{
+    for (HaloPeer &h : g_halo) { dev_free(h.sendIdx); dev_free(h.recvIdx); dev_free(h.sendBuf); dev_free(h.recvBuf); }
+    g_halo.clear();
+}
+void comm_finalize()
+{
+    comm_clear_halo();
+    if (g_comm) { nccl.CommDestroy(g_comm); g_comm = nullptr; }
+    g_world = 1; g_rank = 0;
+}
+void comm_add_halo_peer(int peer, uint32_t nSend, const uint32_t *sendIdx, uint32_t nRecv, const uint32_t *recvIdx)
+{
+    HaloPeer h{};
+    h.peer = peer; h.nSend = nSend; h.nRecv = nRecv;
+    h.sendIdx = (uint32_t *)dev_alloc((size_t)nSend * 4); h.recvIdx = (uint32_t *)dev_alloc((size_t)nRecv * 4);
+    h.sendBuf = (double *)dev_alloc((size_t)nSend * 8); h.recvBuf = (double *)dev_alloc((size_t)nRecv * 8);
+    if (nSend) h2d(h.sendIdx, sendIdx, (size_t)nSend * 4);
+    if (nRecv) h2d(h.recvIdx, recvIdx, (size_t)nRecv * 4);
+    g_halo.push_back(h);
+}
+void comm_allreduce(double *devValues, int count, bool isMax)
+{
+    if (g_world <= 1) return;
+    NCCL_OK(nccl.AllReduce(devValues, devValues, (size_t)count, NCCL_FLOAT64, isMax ? NCCL_MAX : NCCL_SUM, g_comm, g_stream));
+}
+void comm_halo(double *x)
+{
+    if (g_world <= 1 || g_halo.empty()) return;
+    for (HaloPeer &h : g_halo)
+        if (h.nSend) { kern_pack<<<reduce_blocks(h.nSend), SF3D_BLOCK, 0, g_stream>>>(x, h.sendIdx, h.nSend, h.sendBuf); LAUNCH_CHECK(); }
+    NCCL_OK(nccl.GroupStart());
+    for (HaloPeer &h : g_halo)
+    {
+        if (h.nSend) NCCL_OK(nccl.Send(h.sendBuf, h.nSend, NCCL_FLOAT64, h.peer, g_comm, g_stream));
+        if (h.nRecv) NCCL_OK(nccl.Recv(h.recvBuf, h.nRecv, NCCL_FLOAT64, h.peer, g_comm, g_stream));
+    }
+    NCCL_OK(nccl.GroupEnd());
+    for (HaloPeer &h : g_halo)
+        if (h.nRecv) { kern_unpack<<<reduce_blocks(h.nRecv), SF3D_BLOCK, 0, g_stream>>>(x, h.recvIdx, h.nRecv, h.recvBuf); LAUNCH_CHECK(); }
+}
+
+// ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
 #define GRID(n) reduce_blocks(n), SF3D_BLOCK, 0, g_stream
@@ -566,13 +725,46 @@ void k_link_geometry(const SF3DView &v, int *surfaceOrderOk)
 void k_begin_try(const SF3DView &v) { ProfScope ps(SF3D_K_BEGIN_TRY); kern_begin_try<<<GRID(v.N)>>>(v); LAUNCH_CHECK(); }
 void k_restore_old(const SF3DView &v) { ProfScope ps(SF3D_K_OTHER); kern_restore_old<<<GRID(v.N)>>>(v); LAUNCH_CHECK(); }
 void k_node_phase(const SF3DView &v, double dt, int withCapacity) { ProfScope ps(SF3D_K_NODE_PHASE); kern_node_phase<<<GRID(v.N)>>>(v, dt, withCapacity); LAUNCH_CHECK(); }
-void k_assemble(const SF3DView &v, double dt, int approx, double dtMin) { ProfScope ps(SF3D_K_ASSEMBLE); kern_assemble<<<GRID(v.N)>>>(v, dt, approx, dtMin); LAUNCH_CHECK(); }
+void k_assemble(const SF3DView &v, double dt, int approx, double dtMin)
+{
+    { ProfScope ps(SF3D_K_ASSEMBLE); kern_assemble<<<GRID(v.N)>>>(v, dt, approx, dtMin); LAUNCH_CHECK(); }
+    if (v.world > 1)
+    {
+        comm_allreduce(v.ctrl->red, 1, true);
+        kern_rule_courant<<<1, 1, 0, g_stream>>>(v.ctrl, dt, dtMin); LAUNCH_CHECK();
+    }
+}
 void k_jacobi(const SF3DView &v, const double *xin, double *xout, int maxIter, double tol)
-{ ProfScope ps(SF3D_K_JACOBI); kern_jacobi<<<GRID(v.N)>>>(v, xin, xout, maxIter, tol); LAUNCH_CHECK(); }
-void k_post(const SF3DView &v, const double *x, double dt, int mode) { ProfScope ps(SF3D_K_POST); kern_post<<<GRID(v.N)>>>(v, x, dt, mode); LAUNCH_CHECK(); }
+{
+    { ProfScope ps(SF3D_K_JACOBI); kern_jacobi<<<GRID(v.N)>>>(v, xin, xout, maxIter, tol); LAUNCH_CHECK(); }
+    if (v.world > 1)
+    {
+        ProfScope ps(SF3D_K_OTHER);
+        comm_halo(xout);                                 // boundary rows of x -> neighbours' ghost rows
+        comm_allreduce(v.ctrl->red, 1, false);           // residual sum over ranks
+        kern_rule_jacobi<<<1, 1, 0, g_stream>>>(v.ctrl, v.nGlobal, maxIter, tol); LAUNCH_CHECK();
+    }
+}
+void k_post(const SF3DView &v, const double *x, double dt, int mode)
+{
+    { ProfScope ps(SF3D_K_POST); kern_post<<<GRID(v.N)>>>(v, x, dt, mode); LAUNCH_CHECK(); }
+    if (v.world > 1)
+    {
+        comm_allreduce(v.ctrl->red, 2, false);
+        kern_rule_post<<<1, 1, 0, g_stream>>>(v.ctrl); LAUNCH_CHECK();
+    }
+}
 void k_accept(const SF3DView &v, double dt) { ProfScope ps(SF3D_K_ACCEPT); kern_accept<<<GRID(v.N)>>>(v, dt); LAUNCH_CHECK(); }
 void k_restore_best(const SF3DView &v) { ProfScope ps(SF3D_K_OTHER); kern_restore_best<<<GRID(v.N)>>>(v); LAUNCH_CHECK(); }
-void k_total_boundary_flow(const SF3DView &v, uint32_t bt) { kern_total_boundary<<<GRID(v.N)>>>(v, bt); LAUNCH_CHECK(); }
+void k_total_boundary_flow(const SF3DView &v, uint32_t bt)
+{
+    kern_total_boundary<<<GRID(v.N)>>>(v, bt); LAUNCH_CHECK();
+    if (v.world > 1)
+    {
+        comm_allreduce(v.ctrl->red, 1, false);
+        kern_rule_boundary<<<1, 1, 0, g_stream>>>(v.ctrl); LAUNCH_CHECK();
+    }
+}
 void k_set_potential(const SF3DView &v, uint32_t first, uint32_t count, const double *src, int isTotal)
 { if (count) { kern_set_potential<<<GRID(count)>>>(v, first, count, src, isTotal); LAUNCH_CHECK(); } }
 void k_get_field(const SF3DView &v, int field, uint32_t first, uint32_t count, double *dst)

@@ -24,12 +24,14 @@ enum : uint32_t { BT_NONE = 0, BT_RUNOFF = 1, BT_FREE_DRAINAGE = 2, BT_FREE_LATE
                   BT_URBAN = 5, BT_ROAD = 6, BT_CULVERT = 7, BT_HEAT_SURFACE = 8, BT_SOLUTE = 9 };
 
 // meta word per node:  bits 0-3 boundary type | bit 4 surface flag | bits 5-8 numLateralLink |
-//                      bits 9-18 link-present mask in SLOT order (slot 0 Up, 1 Down, 2.. Lateral)
+//                      bits 9-18 link-present mask in SLOT order (slot 0 Up, 1 Down, 2.. Lateral) |
+//                      bit 19 ghost flag
 #define META_BT(m)        ((m) & 0xFu)
 #define META_SURFACE(m)   (((m) >> 4) & 1u)
 #define META_NLAT(m)      (((m) >> 5) & 0xFu)
 #define META_LINKMASK(m)  (((m) >> 9) & 0x3FFu)
 #define META_HAS_SLOT(m, s) (((m) >> (9 + (s))) & 1u)
+#define META_GHOST(m)     (((m) >> 19) & 1u)   // halo copy of a node owned by another rank (multi-GPU slabs)
 
 // Matrix columns are stored in the reference's COLUMN order, which fixes the floating-point
 // summation order of the Jacobi row (cpusolver.cpp:352-374): column 0 = Up (slot 0),
@@ -72,10 +74,13 @@ struct Ctrl {
     int    sweeps;          // sweeps executed in the current solve
     unsigned int ticket;    // last-block election counter
     int    pad;
+    double red[4];          // multi-GPU: local reductions handed to the all-reduce before the rule is applied
 };
 
 struct SF3DView {
-    uint32_t N, Ns;                 // nodes, surface nodes
+    uint32_t N, Ns;                 // nodes, surface nodes (local, ghosts included)
+    uint32_t world;                 // number of ranks sharing the catchment (1 = single GPU)
+    double   nGlobal;               // owned nodes summed over ranks (= N when world == 1)
     // flags (simulationFlags_t, types.h:188-197)
     int computeHeat, computeHeatVapor, computeHeatAdvection, hfSaveMode;
     // solver parameters needed on device

@@ -1,0 +1,98 @@
+"""Row-slab partition of a DEM catchment over the GPUs of one box.
+
+All layers of a cell column live on the same rank (vertical links never cross); lateral links reach
+at most one DEM row, so each rank holds its owned rows plus ONE ghost row per neighbouring slab.
+The local raster (ghost rows included) is an ordinary catchment for the library; this module only
+produces the integer maps: owned row ranges, local<->global node ids, and the halo send/recv lists
+(bit-exact index work, tested on CPU with gloo in tests/test_partition.py)."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+from .synth import Catchment
+
+
+def slab_rows(rows: int, world: int, rank: int) -> tuple[int, int]:
+    """Owned DEM rows [r0, r1) of `rank`: contiguous, sizes differ by at most one row."""
+    base, extra = divmod(rows, world)
+    r0 = rank * base + min(rank, extra)
+    return r0, r0 + base + (1 if rank < extra else 0)
+
+
+@dataclass
+class Slab:
+    rank: int
+    world: int
+    rows: int                 # global DEM rows
+    cols: int
+    layers: int               # surface + soil layers
+    r0: int                   # first owned global row
+    r1: int                   # one past the last owned global row
+    top_ghost: int            # 1 if a ghost row precedes the owned rows
+    bottom_ghost: int
+
+    @property
+    def local_row0(self) -> int:
+        return self.r0 - self.top_ghost
+
+    @property
+    def local_rows(self) -> int:
+        return (self.r1 - self.r0) + self.top_ghost + self.bottom_ghost
+
+    @property
+    def n_local(self) -> int:
+        return self.layers * self.local_rows * self.cols
+
+    @property
+    def n_owned(self) -> int:
+        return self.layers * (self.r1 - self.r0) * self.cols
+
+    @property
+    def n_global(self) -> int:
+        return self.layers * self.rows * self.cols
+
+    # ---- integer maps ------------------------------------------------------------------
+    def local_row_nodes(self, local_row: int) -> np.ndarray:
+        """local node ids of one local DEM row, all layers, layer-major"""
+        per_layer = self.local_rows * self.cols
+        base = local_row * self.cols + np.arange(self.cols, dtype=np.int64)
+        return (np.arange(self.layers, dtype=np.int64)[:, None] * per_layer + base[None, :]).reshape(-1).astype(np.uint32)
+
+    def local_to_global(self) -> np.ndarray:
+        """global node id of every local node (ghosts included)"""
+        lay, row, col = np.meshgrid(np.arange(self.layers, dtype=np.int64),
+                                    np.arange(self.local_rows, dtype=np.int64) + self.local_row0,
+                                    np.arange(self.cols, dtype=np.int64), indexing="ij")
+        return (lay * (self.rows * self.cols) + row * self.cols + col).reshape(-1)
+
+    def owned_mask(self) -> np.ndarray:
+        m = np.zeros((self.layers, self.local_rows, self.cols), bool)
+        m[:, self.top_ghost: self.top_ghost + (self.r1 - self.r0), :] = True
+        return m.reshape(-1)
+
+    def halo(self):
+        """(peers, send_lists, recv_lists): for each neighbouring rank the owned boundary row to send
+        and the ghost row to receive, as local node ids (all layers)."""
+        peers, send, recv = [], [], []
+        if self.top_ghost:
+            peers.append(self.rank - 1)
+            send.append(self.local_row_nodes(self.top_ghost))            # first owned row
+            recv.append(self.local_row_nodes(0))                          # ghost row above
+        if self.bottom_ghost:
+            peers.append(self.rank + 1)
+            send.append(self.local_row_nodes(self.local_rows - 1 - self.bottom_ghost))   # last owned row
+            recv.append(self.local_row_nodes(self.local_rows - 1))       # ghost row below
+        return peers, send, recv
+
+
+def make_slab(rows: int, cols: int, n_soil_layers: int, world: int, rank: int) -> Slab:
+    r0, r1 = slab_rows(rows, world, rank)
+    return Slab(rank=rank, world=world, rows=rows, cols=cols, layers=n_soil_layers + 1, r0=r0, r1=r1,
+                top_ghost=1 if rank > 0 else 0, bottom_ghost=1 if rank < world - 1 else 0)
+
+
+def slab_catchment(slab: Slab, **kw) -> Catchment:
+    """The local raster of a slab: the same seeded generator evaluated on the slab's global rows."""
+    return Catchment(slab.local_rows, slab.cols, slab.layers - 1, row0=slab.local_row0, global_rows=slab.rows, **kw)

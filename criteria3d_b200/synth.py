@@ -96,6 +96,8 @@ class Catchment:
     saturated_bottom: bool = False       # C4: lower third of the layers start at psi = +0.1 m
     seed: int = SEED
     initial_psi: float = -2.0
+    row0: int = 0                        # first global DEM row of this (slab of the) raster
+    global_rows: int | None = None       # rows of the whole catchment (None: this raster is the whole)
     # filled by __post_init__
     dem: np.ndarray = field(init=False, repr=False)
     slope_tan: np.ndarray = field(init=False, repr=False)
@@ -110,19 +112,23 @@ class Catchment:
 
     def __post_init__(self):
         R, Cc, cell = self.rows, self.cols, self.cell
-        r = np.arange(R, dtype=np.float64)[:, None]
+        RG = self.global_rows if self.global_rows is not None else R      # generator works in global rows
+        r = (self.row0 + np.arange(R, dtype=np.float64))[:, None]
         c = np.arange(Cc, dtype=np.float64)[None, :]
-        ri = np.arange(R, dtype=np.int64)[:, None] + np.zeros((1, Cc), np.int64)
+        ri = (self.row0 + np.arange(R, dtype=np.int64))[:, None] + np.zeros((1, Cc), np.int64)
         ci = np.arange(Cc, dtype=np.int64)[None, :] + np.zeros((R, 1), np.int64)
         u = _hash01(self.seed, ri, ci)
-        z = (200.0 + cell * (0.03 * (R - 1 - r) + 0.01 * c)
+        z = (200.0 + cell * (0.03 * (RG - 1 - r) + 0.01 * c)
              + 5.0 * np.sin(2 * np.pi * r / 257.0) * np.cos(2 * np.pi * c / 193.0) + 0.25 * u)
         self.dem = np.ascontiguousarray(z, dtype=np.float32)
-        gy, gx = np.gradient(self.dem.astype(np.float64), cell)
+        # analytic slope of the smooth part of the DEM (independent of how the raster is cut into slabs)
+        gy = -0.03 + 5.0 * (2 * np.pi / 257.0 / cell) * np.cos(2 * np.pi * r / 257.0) * np.cos(2 * np.pi * c / 193.0)
+        gx = 0.01 - 5.0 * (2 * np.pi / 193.0 / cell) * np.sin(2 * np.pi * r / 257.0) * np.sin(2 * np.pi * c / 193.0)
         self.slope_tan = np.ascontiguousarray(np.sqrt(gx * gx + gy * gy), dtype=np.float32)
         self.cell_rank = np.arange(R * Cc, dtype=np.int32).reshape(R, Cc)
         self.outlet = np.zeros((R, Cc), np.uint8)
-        self.outlet[R - 1, :] = 1                       # outlet edge = last row
+        if self.row0 + R == RG:
+            self.outlet[R - 1, :] = 1                   # outlet edge = last row of the whole catchment
         self.soil_id = (np.floor(_hash01(self.seed + 1, ri // 64, ci // 64) * 4).astype(np.uint16) % 4)
         rough = _hash01(self.seed + 2, ri, ci) < 0.10
         self.surface_id = np.ascontiguousarray(rough.astype(np.uint16))
@@ -151,7 +157,8 @@ class Catchment:
     def grid_desc(self) -> GridDesc:
         d = GridDesc()
         d.rows, d.cols, d.layers, d.n_valid = self.rows, self.cols, self.layers, self.n_surface
-        d.cell, d.x_ll, d.y_ll = self.cell, 0.0, 0.0
+        RG = self.global_rows if self.global_rows is not None else self.rows
+        d.cell, d.x_ll, d.y_ll = self.cell, 0.0, self.cell * (RG - self.row0 - self.rows)
         d.dem = self.dem.ctypes.data_as(C.POINTER(C.c_float))
         d.slope_tan = self.slope_tan.ctypes.data_as(C.POINTER(C.c_float))
         d.cell_rank = self.cell_rank.ctypes.data_as(C.POINTER(C.c_int32))

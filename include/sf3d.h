@@ -255,6 +255,20 @@ uint8_t sf3d_ext_reset_solver(void);
  * two libraries return SF3D_PARAMETER_ERROR. */
 uint8_t sf3d_ext_set_device(int device);
 
+/* product only: row-slab partition of one catchment over several GPUs, one process per GPU.
+ * Each rank initialises its slab (owned DEM rows plus one ghost row per neighbour) as an ordinary
+ * catchment, then declares which local nodes are ghosts (recv lists) and which owned nodes the
+ * neighbours need (send lists).  The library exchanges x on those lists after every Jacobi sweep
+ * and all-reduces the residual, Courant and balance sums (NCCL over NVLink).
+ * The 128-byte id is an ncclUniqueId: rank 0 creates it, the harness broadcasts it. */
+uint8_t sf3d_ext_comm_unique_id(uint8_t id[128]);
+uint8_t sf3d_ext_comm_init(int rank, int world, const uint8_t id[128]);
+uint8_t sf3d_ext_comm_finalize(void);
+uint8_t sf3d_ext_set_halo(uint32_t n_peers, const int32_t *peers,
+                          const uint32_t *send_count, const uint32_t *send_idx,   /* concatenated per peer */
+                          const uint32_t *recv_count, const uint32_t *recv_idx,
+                          uint64_t n_global_nodes);
+
 /* product only: the cudaStream_t every kernel of the library is launched on (for CUDA-event
  * timing from the harness); NULL in the CPU libraries. */
 void *sf3d_ext_stream(void);

@@ -256,6 +256,11 @@ uint8_t sf3d_ext_get_counters(sf3d_counters *out)
 uint8_t sf3d_ext_reset_counters(void) { std::memset(&g_cnt, 0, sizeof g_cnt); return SF3D_OK; }
 const char *sf3d_ext_backend(void) { return "reference"; }
 uint8_t sf3d_ext_set_device(int) { return SF3D_PARAMETER_ERROR; }
+uint8_t sf3d_ext_comm_unique_id(uint8_t id[128]) { (void)id; return SF3D_PARAMETER_ERROR; }
+uint8_t sf3d_ext_comm_init(int rank, int world, const uint8_t id[128]) { (void)rank; (void)world; (void)id; return SF3D_PARAMETER_ERROR; }
+uint8_t sf3d_ext_comm_finalize(void) { return SF3D_PARAMETER_ERROR; }
+uint8_t sf3d_ext_set_halo(uint32_t n, const int32_t *p, const uint32_t *sc, const uint32_t *si, const uint32_t *rc, const uint32_t *ri, uint64_t ng)
+{ (void)n; (void)p; (void)sc; (void)si; (void)rc; (void)ri; (void)ng; return SF3D_PARAMETER_ERROR; }
 void *sf3d_ext_stream(void) { return nullptr; }
 uint8_t sf3d_ext_profile(int) { return SF3D_PARAMETER_ERROR; }
 uint8_t sf3d_ext_get_kernel_times(sf3d_kernel_times *) { return SF3D_PARAMETER_ERROR; }

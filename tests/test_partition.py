@@ -1,0 +1,114 @@
+"""CPU tests of the row-slab partition (integer maps must be bit-exact) and of the halo lists over a
+real 2-process gloo group (the N>1 host logic; the device side is exercised on the GPU box)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from criteria3d_b200 import ORACLE_LIB, SoilFluxes3D
+from criteria3d_b200.partition import make_slab, slab_catchment, slab_rows
+from criteria3d_b200.synth import Catchment, setup
+
+
+@pytest.mark.parametrize("rows,world", [(7, 2), (64, 8), (1024, 3), (5, 5)])
+def test_slab_rows_cover_the_dem_once(rows, world):
+    spans = [slab_rows(rows, world, r) for r in range(world)]
+    assert spans[0][0] == 0 and spans[-1][1] == rows
+    for a, b in zip(spans, spans[1:]):
+        assert a[1] == b[0]
+    sizes = [b - a for a, b in spans]
+    assert max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_local_graph_equals_global_graph_on_owned_nodes(world):
+    """Build the whole catchment and every slab with the CPU oracle: for every OWNED node the link
+    slot table, mapped to global ids, and the geometry are identical to the global build."""
+    if not ORACLE_LIB.exists():
+        pytest.skip("oracle library not built")
+    sf = SoilFluxes3D(ORACLE_LIB)
+    R, C, L = 13, 9, 3
+    cat = Catchment(R, C, L)
+    setup(sf, cat, threads=1)
+    g_tab = [sf.link_table(s, 0, cat.n_nodes) for s in range(10)]
+    g_meta = sf.node_meta(0, cat.n_nodes)
+    g_psi = sf.get_field(3, 0, cat.n_nodes)
+    g_H = sf.get_field(4, 0, cat.n_nodes)
+    owned_total = 0
+    for rank in range(world):
+        slab = make_slab(R, C, L, world, rank)
+        lc = slab_catchment(slab)
+        setup(sf, lc, threads=1)
+        l2g = slab.local_to_global()
+        own = slab.owned_mask()
+        owned_total += int(own.sum())
+        assert slab.n_local == lc.n_nodes and int(own.sum()) == slab.n_owned
+        for s in range(10):
+            lt, li, ar = sf.link_table(s, 0, lc.n_nodes)
+            assert np.array_equal(lt[own], g_tab[s][0][l2g[own]]), (rank, s)
+            has = own & (lt != 0)
+            assert np.array_equal(l2g[li[has]], g_tab[s][1][l2g[has]].astype(np.int64)), (rank, s)
+            assert np.array_equal(ar[has], g_tab[s][2][l2g[has]])
+        for a, b in zip(sf.node_meta(0, lc.n_nodes), g_meta):
+            assert np.array_equal(a[own], b[l2g[own]])
+        assert np.array_equal(sf.get_field(4, 0, lc.n_nodes)[own], g_H[l2g[own]])       # z and psi identical
+        assert np.array_equal(sf.get_field(3, 0, lc.n_nodes)[own], g_psi[l2g[own]])
+        # every link of an owned node points to an owned node or to a ghost that some peer sends
+        peers, send, recv = slab.halo()
+        ghosts = set(np.concatenate(recv).tolist()) if recv else set()
+        for s in range(10):
+            lt, li, _ = sf.link_table(s, 0, lc.n_nodes)
+            tgt = li[own & (lt != 0)]
+            assert all(own[t] or (t in ghosts) for t in tgt.tolist())
+    assert owned_total == cat.n_nodes
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _halo_worker(rank, world, port, R, C, L, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    slab = make_slab(R, C, L, world, rank)
+    l2g = slab.local_to_global()
+    own = slab.owned_mask()
+    x = np.where(own, np.sin(l2g * 0.37) + l2g, -1.0)          # ghosts start wrong
+    peers, send, recv = slab.halo()
+    ops, bufs = [], []
+    for p, s_idx, r_idx in zip(peers, send, recv):
+        sb = torch.from_numpy(np.ascontiguousarray(x[s_idx]))
+        rb = torch.empty(len(r_idx), dtype=torch.float64)
+        ops += [dist.P2POp(dist.isend, sb, p), dist.P2POp(dist.irecv, rb, p)]
+        bufs.append((r_idx, rb))
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+    for r_idx, rb in bufs:
+        x[r_idx] = rb.numpy()
+    ok = np.array_equal(x, np.sin(l2g * 0.37) + l2g)
+    n_owned = torch.tensor([float(own.sum())], dtype=torch.float64)
+    dist.all_reduce(n_owned)                                   # what sf3d_ext_set_halo is given as n_global_nodes
+    q.put((rank, bool(ok), float(n_owned.item()), slab.n_global))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_halo_exchange_over_gloo(world):
+    R, C, L = 11, 6, 4
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_halo_worker, args=(r, world, port, R, C, L, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _, _ in res), res
+    assert all(n == ng for _, _, n, ng in res), res
