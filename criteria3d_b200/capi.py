@@ -111,6 +111,9 @@ class Field(enum.IntEnum):  # include/sf3d.h enum sf3d_field
     BOUNDARY_TEMPERATURE = 17
     BOUNDARY_RELATIVE_HUMIDITY = 18
     BOUNDARY_WIND_SPEED = 19
+    BOUNDARY_HEIGHT_WIND = 20
+    BOUNDARY_HEIGHT_TEMPERATURE = 21
+    BOUNDARY_ROUGHNESS = 22
 
 
 # sentinel doubles of getDoubleErrorValue (types.h:42-64)
@@ -134,7 +137,7 @@ class GridDesc(C.Structure):
         ("layer_depth", C.POINTER(C.c_double)), ("layer_thickness", C.POINTER(C.c_double)),
         ("layer_horizon", C.POINTER(C.c_uint16)), ("boundary_l1", C.POINTER(C.c_uint8)),
         ("free_catchment_runoff", C.c_int), ("free_lateral_drainage", C.c_int),
-        ("free_bottom_drainage", C.c_int),
+        ("free_bottom_drainage", C.c_int), ("heat_surface_layer1", C.c_int),
     ]
 
 
@@ -238,6 +241,7 @@ _EXT = [
     ("sf3d_ext_get_link_table", u8, [u8, u32, u32, C.POINTER(u8), C.POINTER(u32), C.POINTER(dbl)]),
     ("sf3d_ext_get_node_meta", u8, [u32, u32, C.POINTER(u8), C.POINTER(u8), C.POINTER(u8)]),
     ("sf3d_ext_build_grid", u8, [C.POINTER(GridDesc)]),
+    ("sf3d_ext_set_fixed_temperature", u8, [u32, u32, C.POINTER(dbl), dbl]),
     ("sf3d_ext_get_counters", u8, [C.POINTER(Counters)]),
     ("sf3d_ext_reset_counters", u8, []),
     ("sf3d_ext_backend", C.c_char_p, []),
@@ -313,6 +317,10 @@ class SoilFluxes3D:
 
     def build_grid(self, desc: GridDesc) -> int:
         return self.lib.sf3d_ext_build_grid(C.byref(desc))
+
+    def set_fixed_temperature(self, first: int, temperature: np.ndarray, depth: float) -> int:
+        t = np.ascontiguousarray(temperature, dtype=np.float64)
+        return self.lib.sf3d_ext_set_fixed_temperature(first, t.size, _ptr(t, dbl), depth)
 
     def counters(self) -> dict:
         c = Counters()

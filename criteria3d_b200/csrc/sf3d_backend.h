@@ -53,6 +53,18 @@ void k_post(const SF3DView &v, const double *x, double dt, int mode);
 void k_accept(const SF3DView &v, double dt);
 void k_restore_best(const SF3DView &v);
 void k_total_boundary_flow(const SF3DView &v, uint32_t boundaryType);
+// coupled heat
+void k_update_conductance(const SF3DView &v);
+void k_save_water_fluxes(const SF3DView &v, double dtHeat, double dtWater);
+void k_reset_water_fluxes(const SF3DView &v);
+void k_boundary_heat(const SF3DView &v, double maxTimeStep);
+void k_heat_begin(const SF3DView &v, double dtHeat, double dtWater);
+void k_heat_assemble(const SF3DView &v, double dtHeat, double dtWater);
+void k_heat_jacobi(const SF3DView &v, const double *xin, double *xout, int maxIter, double tol);
+void k_heat_post(const SF3DView &v, const double *x, double dtHeat, double dtWater, int mode);
+void k_heat_accept(const SF3DView &v, double dtHeat, double dtWater);
+void k_heat_copy_T(const SF3DView &v, int mode);
+void k_halo(double *x);
 void read_ctrl(const SF3DView &v, Ctrl *out);     // async copy to pinned + stream sync
 void write_ctrl(const SF3DView &v, const Ctrl *in);
 
@@ -73,7 +85,7 @@ struct GridDev {
     const uint16_t *layerTab;       // [layers * nSoilIds]: soil-table row of (soil id, layer horizon)
     uint32_t nSoilIds;
     int freeRunoff, freeLateral, freeBottom;
-    int computeWater, computeHeat;
+    int computeWater, computeHeat, heatSurfaceL1;
 };
 void k_build_grid(const SF3DView &v, const GridDev &g);
 

@@ -64,6 +64,13 @@ struct State {
     Mirror<uint16_t> tab;
     Mirror<double> larea, lflow;
     Mirror<double> H, oldH, Se, K, sink, pond;
+    // heat (allocated when isComputeHeat)
+    Mirror<double> T, oldT, hSink;
+    Mirror<double> hbHeightWind, hbHeightT, hbRough, hbAero, hbSoilCond, hbT, hbRH, hbWind, hbNetIrr,
+                   hbSens, hbLat, hbRad, hbAdv, hbFixT, hbFixDepth;
+    Mirror<double> lfluxes;               // [type][slot][node]; 1 type (HeatTotal) unless save mode All (9)
+    int hfTypesAllocated = 0;
+    double *hFlux = nullptr, *lwFlux = nullptr, *lvFlux = nullptr, *hdiag = nullptr;
     // device-only
     double *bestH = nullptr, *SeOld = nullptr, *wFlow = nullptr, *lgeom = nullptr, *mval = nullptr,
            *b = nullptr, *cap = nullptr, *x0 = nullptr, *x1 = nullptr, *partA = nullptr, *partB = nullptr,
@@ -115,6 +122,23 @@ void fill_view()
     v.culverts = S.culverts.empty() ? nullptr : S.dCulv;
     v.culvertOf = S.culverts.empty() ? nullptr : S.culvertOf.d;
     v.ctrl = S.ctrl; v.partA = S.partA; v.partB = S.partB; v.partC = S.partC;
+    if (S.heat)
+    {
+        v.T = S.T.d; v.oldT = S.oldT.d; v.hFlux = S.hFlux; v.hSink = S.hSink.d;
+        v.hbHeightWind = S.hbHeightWind.d; v.hbHeightT = S.hbHeightT.d; v.hbRough = S.hbRough.d; v.hbAero = S.hbAero.d;
+        v.hbSoilCond = S.hbSoilCond.d; v.hbT = S.hbT.d; v.hbRH = S.hbRH.d; v.hbWind = S.hbWind.d; v.hbNetIrr = S.hbNetIrr.d;
+        v.hbSens = S.hbSens.d; v.hbLat = S.hbLat.d; v.hbRad = S.hbRad.d; v.hbAdv = S.hbAdv.d;
+        v.hbFixT = S.hbFixT.d; v.hbFixDepth = S.hbFixDepth.d;
+        v.lwFlux = S.lwFlux; v.lvFlux = S.lvFlux; v.lfluxes = S.lfluxes.d; v.hdiag = S.hdiag;
+    }
+}
+
+Mirror<double> *heat_boundary_mirrors[15];
+void collect_heat_mirrors()
+{
+    Mirror<double> *m[15] = {&S.hbHeightWind, &S.hbHeightT, &S.hbRough, &S.hbAero, &S.hbSoilCond, &S.hbT, &S.hbRH, &S.hbWind,
+                             &S.hbNetIrr, &S.hbSens, &S.hbLat, &S.hbRad, &S.hbAdv, &S.hbFixT, &S.hbFixDepth};
+    for (int k = 0; k < 15; ++k) heat_boundary_mirrors[k] = m[k];
 }
 
 void upload_tables()
@@ -152,6 +176,12 @@ uint8_t sync_to_device(bool finalizeTopology = true)
     S.bSlope.push(); S.bSize.push(); S.bRate.push(); S.bSum.push(); S.bPresc.push();
     S.lidx.push(); S.larea.push(); S.lflow.push(); S.culvertOf.push();
     S.H.push(); S.oldH.push(); S.Se.push(); S.K.push(); S.sink.push(); S.pond.push();
+    if (S.heat)
+    {
+        S.T.push(); S.oldT.push(); S.hSink.push(); S.lfluxes.push();
+        collect_heat_mirrors();
+        for (Mirror<double> *m : heat_boundary_mirrors) m->push();
+    }
     fill_view();
     if (S.topoDirty && finalizeTopology)
     {
@@ -172,6 +202,12 @@ void step_wrote_device()
 {
     S.H.dev_written(); S.oldH.dev_written(); S.Se.dev_written(); S.K.dev_written();
     S.bRate.dev_written(); S.bSum.dev_written(); S.lflow.dev_written();
+    if (S.heat)
+    {
+        S.T.dev_written(); S.oldT.dev_written(); S.lfluxes.dev_written();
+        S.hbAero.dev_written(); S.hbSoilCond.dev_written(); S.hbSens.dev_written(); S.hbLat.dev_written();
+        S.hbRad.dev_written(); S.hbAdv.dev_written();
+    }
 }
 
 // host-side physics for the scalar setters (same row functions, compiled for the host)
@@ -216,6 +252,11 @@ void release_all()
     S.bRate.release(); S.bSum.release(); S.bPresc.release(); S.meta.release(); S.lidx.release();
     S.culvertOf.release(); S.tab.release(); S.larea.release(); S.lflow.release();
     S.H.release(); S.oldH.release(); S.Se.release(); S.K.release(); S.sink.release(); S.pond.release();
+    S.T.release(); S.oldT.release(); S.hSink.release(); S.lfluxes.release();
+    collect_heat_mirrors();
+    for (Mirror<double> *m : heat_boundary_mirrors) m->release();
+    { double **hd[] = {&S.hFlux, &S.lwFlux, &S.lvFlux, &S.hdiag}; for (double **p : hd) { dev_free(*p); *p = nullptr; } }
+    S.hfTypesAllocated = 0;
     double **devOnly[] = {&S.bestH, &S.SeOld, &S.wFlow, &S.lgeom, &S.mval, &S.b, &S.cap, &S.x0, &S.x1,
                           &S.partA, &S.partB, &S.partC, &S.scratch};
     for (double **p : devOnly) { dev_free(*p); *p = nullptr; }
@@ -240,11 +281,6 @@ uint8_t sf3d_initialize(uint32_t nrNodes, uint32_t nrSurfaceNodes, uint8_t nrLat
     return guarded([&]() -> uint8_t {
         uint8_t rc = sf3d_clean();
         if (rc) return rc;
-        if (isComputeHeat)
-        {
-            fprintf(stderr, "[sf3d_b200] coupled heat is not built in this revision of the product\n");
-            return SF3D_PARAMETER_ERROR;
-        }
         dev_select(g_device);
         S.water = isComputeWater != 0; S.heat = isComputeHeat != 0; S.solutes = isComputeSolutes != 0;
         S.heatVapor = S.heatAdvection = false; S.hfMode = 0;
@@ -266,6 +302,16 @@ uint8_t sf3d_initialize(uint32_t nrNodes, uint32_t nrSurfaceNodes, uint8_t nrLat
         const size_t nb = (size_t)reduce_blocks(0xFFFFFFFFu);
         S.partA = (double *)dev_alloc(nb * 8); S.partB = (double *)dev_alloc(nb * 8); S.partC = (double *)dev_alloc(nb * 8);
         S.ctrl = (Ctrl *)dev_alloc(sizeof(Ctrl));
+        if (S.heat)
+        {
+            S.T.alloc(N); S.oldT.alloc(N); S.hSink.alloc(N);
+            collect_heat_mirrors();
+            for (Mirror<double> *m : heat_boundary_mirrors) m->alloc(N);
+            S.hFlux = (double *)dev_alloc(N * 8); S.hdiag = (double *)dev_alloc(N * 8);
+            S.lwFlux = (double *)dev_alloc(L * 8); S.lvFlux = (double *)dev_alloc(L * 8);
+            S.hfTypesAllocated = (S.hfMode == 2) ? 9 : 1;
+            S.lfluxes.alloc((size_t)S.hfTypesAllocated * L);
+        }
 
         S.tablesDirty = S.topoDirty = true;
         S.initialized = true;
@@ -275,6 +321,7 @@ uint8_t sf3d_initialize(uint32_t nrNodes, uint32_t nrSurfaceNodes, uint8_t nrLat
         S.eng = Engine{};
         S.eng.p = &g_params;
         S.eng.computeWater = S.water;
+        S.eng.computeHeat = S.heat;
         fill_view();
         return SF3D_OK;
     }, (uint8_t)SF3D_MEMORY_ERROR);
@@ -289,7 +336,8 @@ uint8_t sf3d_initialize_balance(void)
         if (rc) return rc;
         S.eng.initializeWaterBalance();
         S.lflow.dev_written(); S.bSum.dev_written(); S.Se.dev_written();
-        if (!S.heat) S.eng.wholePeriod.heatMBR = 1.;          // soilFluxes3D.cpp:194
+        if (S.heat) S.eng.initializeHeatBalance();            // soilFluxes3D.cpp:191-192
+        else S.eng.wholePeriod.heatMBR = 1.;                  // soilFluxes3D.cpp:194
         return SF3D_OK;
     }, (uint8_t)SF3D_SOLVER_ERROR);
 }
@@ -308,6 +356,13 @@ uint8_t sf3d_clean(void)
 uint8_t sf3d_initialize_heat_flag(uint8_t saveModeHeat, int adv, int lat)     // soilFluxes3D.cpp:325-332
 {
     S.hfMode = saveModeHeat; S.heatAdvection = adv != 0; S.heatVapor = lat != 0;
+    if (S.initialized && S.heat && S.hfMode == 2 && S.hfTypesAllocated < 9)
+        return guarded([&]() -> uint8_t {
+            S.lfluxes.release();
+            S.hfTypesAllocated = 9;
+            S.lfluxes.alloc((size_t)9 * SF3D_NLINK * S.N);
+            return SF3D_OK;
+        }, (uint8_t)SF3D_MEMORY_ERROR);
     return SF3D_OK;
 }
 
@@ -415,6 +470,12 @@ static uint8_t set_node_boundary_unchecked(uint32_t i, uint8_t bt, double slope,
         S.bSum.rw()[i] = 0.;
         S.bPresc.rw()[i] = SF3D_NODATA;
     }
+    if (S.heat)                                   // soilFluxes3D.cpp:705-722
+    {
+        collect_heat_mirrors();
+        for (Mirror<double> *m : heat_boundary_mirrors) m->rw()[i] = SF3D_NODATA;
+        S.hbRad.rw()[i] = 0.; S.hbLat.rw()[i] = 0.; S.hbSens.rw()[i] = 0.; S.hbAdv.rw()[i] = 0.;
+    }
     return SF3D_OK;
 }
 uint8_t sf3d_set_node_boundary(uint32_t nodeIndex, uint8_t boundaryType, double slope, double boundaryArea)
@@ -456,6 +517,11 @@ uint8_t sf3d_set_node(uint32_t index, double x, double y, double z, double volum
             if (isSurface && index < S.Ns) S.pond.rw()[index] = (double)0.0001f;     // :616 (float literal)
             S.sink.rw()[index] = 0.;
         }
+        if (S.heat && !isSurface)                 // soilFluxes3D.cpp:620-626
+        {
+            S.T.rw()[index] = 273.15 + 20; S.oldT.rw()[index] = 273.15 + 20;
+            S.hSink.rw()[index] = 0.;               // heatFlux is device-only and rebuilt every heat sub-step
+        }
         S.topoDirty = true;
         return SF3D_OK;
     }, (uint8_t)SF3D_MEMORY_ERROR);
@@ -490,6 +556,13 @@ uint8_t sf3d_set_node_link(uint32_t nodeIndex, uint32_t linkIndex, uint8_t direc
         S.lidx.rw()[li] = linkIndex;
         S.larea.rw()[li] = interfaceArea;
         if (S.water) S.lflow.rw()[li] = 0.;
+        if (S.heat)                                   // soilFluxes3D.cpp:669-678 (waterFlux/vaporFlux are zero-initialised on the device)
+        {
+            double *fx = S.lfluxes.rw();
+            fx[li] = SF3D_NODATA;
+            if (S.hfMode == 2 && S.hfTypesAllocated == 9)
+                for (int t = 1; t < 9; ++t) fx[(size_t)t * SF3D_NLINK * S.N + li] = SF3D_NODATA;
+        }
         S.topoDirty = true;
         return SF3D_OK;
     }, (uint8_t)SF3D_MEMORY_ERROR);
@@ -687,30 +760,107 @@ double sf3d_get_total_water_content(void)
 double sf3d_get_water_storage(void) { return S.eng.curStep.waterStorage; }
 double sf3d_get_water_mbr(void) { return S.eng.wholePeriod.waterMBR; }
 
-// ---- heat API (soilFluxes3D.cpp:1283-1753): heat milestone ------------------------------------------------------------------
-#define HEAT_SETTER(name) uint8_t name(uint32_t i, double) { REQUIRE_INIT_E(); REQUIRE_INDEX_E(i); return SF3D_MISSING_DATA_ERROR; }
-HEAT_SETTER(sf3d_set_node_heat_sink_source)
-HEAT_SETTER(sf3d_set_node_temperature)
-HEAT_SETTER(sf3d_set_node_boundary_height_wind)
-HEAT_SETTER(sf3d_set_node_boundary_height_temperature)
-HEAT_SETTER(sf3d_set_node_boundary_net_irradiance)
-HEAT_SETTER(sf3d_set_node_boundary_temperature)
-HEAT_SETTER(sf3d_set_node_boundary_relative_humidity)
-HEAT_SETTER(sf3d_set_node_boundary_roughness)
-HEAT_SETTER(sf3d_set_node_boundary_wind_speed)
-uint8_t sf3d_set_node_boundary_fixed_temperature(uint32_t i, double, double) { REQUIRE_INIT_E(); REQUIRE_INDEX_E(i); return SF3D_MISSING_DATA_ERROR; }
-#define HEAT_GETTER(name, code) double name(uint32_t i) { REQUIRE_INIT_D(); REQUIRE_INDEX_D(i); return err_value(code); }
-HEAT_GETTER(sf3d_get_node_temperature, SF3D_TOPOGRAPHY_ERROR)           // !isHeatNode -> TopographyError (:1494)
-HEAT_GETTER(sf3d_get_node_heat_conductivity, SF3D_TOPOGRAPHY_ERROR)
-HEAT_GETTER(sf3d_get_node_vapor, SF3D_MISSING_DATA_ERROR)
-HEAT_GETTER(sf3d_get_node_boundary_advective_flux, SF3D_MISSING_DATA_ERROR)
-HEAT_GETTER(sf3d_get_node_boundary_latent_flux, SF3D_MISSING_DATA_ERROR)
-HEAT_GETTER(sf3d_get_node_boundary_radiative_flux, SF3D_MISSING_DATA_ERROR)
-HEAT_GETTER(sf3d_get_node_boundary_sensible_flux, SF3D_MISSING_DATA_ERROR)
-HEAT_GETTER(sf3d_get_node_boundary_aerodynamic_conductance, SF3D_MISSING_DATA_ERROR)
-HEAT_GETTER(sf3d_get_node_boundary_soil_conductance, SF3D_MISSING_DATA_ERROR)
-double sf3d_get_node_heat_storage(uint32_t i, double) { REQUIRE_INIT_D(); REQUIRE_INDEX_D(i); return err_value(SF3D_MISSING_DATA_ERROR); }
-double sf3d_get_node_heat_max_flux(uint32_t i, uint8_t, uint8_t) { REQUIRE_INIT_D(); REQUIRE_INDEX_D(i); return err_value(SF3D_TOPOGRAPHY_ERROR); }
+// ---- heat API (soilFluxes3D.cpp:1283-1753) ---------------------------------------------------------------------------------
+#define REQUIRE_HEAT_E() do { if (!S.heat) return SF3D_MISSING_DATA_ERROR; } while (0)   /* the reference would touch null arrays */
+static SF3DView host_view()
+{
+    // a view over the HOST mirrors for the getters that evaluate closures on one node
+    SF3DView v = S.eng.v;
+    v.z = const_cast<double *>(S.z.ro()); v.size = const_cast<double *>(S.size.ro());
+    v.tab = const_cast<uint16_t *>(S.tab.ro()); v.meta = const_cast<uint32_t *>(S.meta.ro());
+    v.H = const_cast<double *>(S.H.ro()); v.oldH = const_cast<double *>(S.oldH.ro());
+    v.T = const_cast<double *>(S.T.ro()); v.oldT = const_cast<double *>(S.oldT.ro());
+    v.soil = S.soils.data();
+    v.wrcModel = g_params.wrcModel;
+    v.computeHeatVapor = S.heatVapor;
+    return v;
+}
+uint8_t sf3d_set_node_heat_sink_source(uint32_t i, double q)
+{ return guarded([&]() -> uint8_t { REQUIRE_INIT_E(); REQUIRE_INDEX_E(i); REQUIRE_HEAT_E(); S.hSink.rw()[i] = q; return SF3D_OK; }, (uint8_t)SF3D_MEMORY_ERROR); }
+uint8_t sf3d_set_node_temperature(uint32_t i, double T)
+{ return guarded([&]() -> uint8_t { REQUIRE_INIT_E(); REQUIRE_INDEX_E(i); REQUIRE_HEAT_E(); S.T.rw()[i] = T; S.oldT.rw()[i] = T; return SF3D_OK; }, (uint8_t)SF3D_MEMORY_ERROR); }
+uint8_t sf3d_set_node_boundary_fixed_temperature(uint32_t i, double T, double depth)
+{
+    return guarded([&]() -> uint8_t {
+        REQUIRE_INIT_E(); REQUIRE_INDEX_E(i); REQUIRE_HEAT_E();
+        const uint32_t bt = node_bt(i);
+        if (bt != BT_PRESCRIBED && bt != BT_FREE_DRAINAGE) return SF3D_BOUNDARY_ERROR;
+        S.hbFixT.rw()[i] = T; S.hbFixDepth.rw()[i] = depth;
+        return SF3D_OK;
+    }, (uint8_t)SF3D_MEMORY_ERROR);
+}
+#define HEAT_BOUNDARY_SETTER(name, mirror, extraCheck)                                              \
+    uint8_t name(uint32_t i, double value)                                                         \
+    {                                                                                              \
+        return guarded([&]() -> uint8_t {                                                          \
+            REQUIRE_INIT_E(); REQUIRE_INDEX_E(i); REQUIRE_HEAT_E();                                \
+            if (node_bt(i) == BT_NONE) return SF3D_BOUNDARY_ERROR;                                 \
+            extraCheck                                                                             \
+            S.mirror.rw()[i] = value;                                                              \
+            return SF3D_OK;                                                                        \
+        }, (uint8_t)SF3D_MEMORY_ERROR);                                                            \
+    }
+HEAT_BOUNDARY_SETTER(sf3d_set_node_boundary_height_wind, hbHeightWind, )
+HEAT_BOUNDARY_SETTER(sf3d_set_node_boundary_height_temperature, hbHeightT, )
+HEAT_BOUNDARY_SETTER(sf3d_set_node_boundary_net_irradiance, hbNetIrr, )
+HEAT_BOUNDARY_SETTER(sf3d_set_node_boundary_temperature, hbT, )
+HEAT_BOUNDARY_SETTER(sf3d_set_node_boundary_relative_humidity, hbRH, )
+HEAT_BOUNDARY_SETTER(sf3d_set_node_boundary_roughness, hbRough, if (value < 0) return SF3D_PARAMETER_ERROR;)
+HEAT_BOUNDARY_SETTER(sf3d_set_node_boundary_wind_speed, hbWind, if ((value < 0.) || (value > 1000.)) return SF3D_PARAMETER_ERROR;)
+
+static bool is_heat_node(uint32_t i) { return S.heat && !is_surface(i); }       // heat.cpp:26-29
+double sf3d_get_node_temperature(uint32_t i)
+{ GUARDED_D( GETTER_PROLOGUE(i); if (!is_heat_node(i)) return err_value(SF3D_TOPOGRAPHY_ERROR); return S.T.ro()[i]; ); }
+double sf3d_get_node_heat_conductivity(uint32_t i)
+{ GUARDED_D( GETTER_PROLOGUE(i); if (!is_heat_node(i)) return err_value(SF3D_TOPOGRAPHY_ERROR);
+    const SF3DView hv = host_view();
+    return h_soil_heat_conductivity(hv, i, hv.T[i], hv.H[i] - hv.z[i]); ); }
+double sf3d_get_node_vapor(uint32_t i)
+{ GUARDED_D( GETTER_PROLOGUE(i);
+    if (!S.water || !S.heat || !S.heatVapor) return err_value(SF3D_MISSING_DATA_ERROR);
+    return h_vapor_from_psi_temp(S.H.ro()[i] - S.z.ro()[i], S.T.ro()[i]); ); }
+double sf3d_get_node_heat_storage(uint32_t i, double h)
+{ GUARDED_D( GETTER_PROLOGUE(i); if (!S.heat) return err_value(SF3D_MISSING_DATA_ERROR);
+    const SF3DView hv = host_view();
+    return h_node_heat_storage(hv, i, h); ); }
+static double link_heat_flux(uint32_t slot, uint32_t i, uint8_t fluxType)        // getLinkHeatFlux, heat.cpp:623-641
+{
+    if (!S.heat) return SF3D_NODATA;
+    if (S.hfMode == 1) return (fluxType == 0) ? S.lfluxes.ro()[(size_t)slot * S.N + i] : SF3D_NODATA;
+    if (S.hfMode == 2 && S.hfTypesAllocated == 9) return S.lfluxes.ro()[((size_t)fluxType * SF3D_NLINK + slot) * S.N + i];
+    return SF3D_NODATA;
+}
+double sf3d_get_node_heat_max_flux(uint32_t i, uint8_t direction, uint8_t fluxType)
+{ GUARDED_D( GETTER_PROLOGUE(i); if (!is_heat_node(i)) return err_value(SF3D_TOPOGRAPHY_ERROR);
+    if (fluxType > 8) return err_value(SF3D_INDEX_ERROR);
+    switch (direction)
+    {
+        case 1: return link_heat_flux(0, i, fluxType);
+        case 2: return link_heat_flux(1, i, fluxType);
+        case 3:
+        {
+            double mx = 0.;
+            for (uint32_t l = 0; l < SF3D_MAX_LATERAL_LINK; ++l)
+            {
+                const double f = link_heat_flux(2 + l, i, fluxType);
+                if (f > fabs(mx)) mx = f;
+            }
+            return mx;
+        }
+        default: return err_value(SF3D_INDEX_ERROR);
+    } ); }
+#define HEAT_BOUNDARY_GETTER(name, mirror, needVapor)                                               \
+    double name(uint32_t i)                                                                        \
+    { GUARDED_D( GETTER_PROLOGUE(i);                                                                \
+        if (needVapor ? (!S.water || !S.heat || !S.heatVapor) : !S.heat) return err_value(SF3D_MISSING_DATA_ERROR); \
+        if (node_bt(i) != BT_HEAT_SURFACE) return err_value(SF3D_BOUNDARY_ERROR);                  \
+        return S.mirror.ro()[i]; ); }
+HEAT_BOUNDARY_GETTER(sf3d_get_node_boundary_advective_flux, hbAdv, true)
+HEAT_BOUNDARY_GETTER(sf3d_get_node_boundary_latent_flux, hbLat, true)
+HEAT_BOUNDARY_GETTER(sf3d_get_node_boundary_radiative_flux, hbRad, false)
+HEAT_BOUNDARY_GETTER(sf3d_get_node_boundary_sensible_flux, hbSens, false)
+HEAT_BOUNDARY_GETTER(sf3d_get_node_boundary_aerodynamic_conductance, hbAero, false)
+HEAT_BOUNDARY_GETTER(sf3d_get_node_boundary_soil_conductance, hbSoilCond, false)
 double sf3d_get_heat_mbr(void) { return S.eng.wholePeriod.heatMBR; }
 double sf3d_get_heat_mbe(void) { return S.eng.wholePeriod.heatMBE; }
 
@@ -809,6 +959,9 @@ uint8_t sf3d_ext_set_field(int field, uint32_t first, uint32_t count, const doub
                 case SF3D_F_BOUNDARY_TEMPERATURE:       rc = sf3d_set_node_boundary_temperature(i, src[k]); break;
                 case SF3D_F_BOUNDARY_RELATIVE_HUMIDITY: rc = sf3d_set_node_boundary_relative_humidity(i, src[k]); break;
                 case SF3D_F_BOUNDARY_WIND_SPEED:        rc = sf3d_set_node_boundary_wind_speed(i, src[k]); break;
+                case SF3D_F_BOUNDARY_HEIGHT_WIND:       rc = sf3d_set_node_boundary_height_wind(i, src[k]); break;
+                case SF3D_F_BOUNDARY_HEIGHT_TEMPERATURE: rc = sf3d_set_node_boundary_height_temperature(i, src[k]); break;
+                case SF3D_F_BOUNDARY_ROUGHNESS:         rc = sf3d_set_node_boundary_roughness(i, src[k]); break;
                 default: return SF3D_PARAMETER_ERROR;
             }
             if (rc && !firstErr) firstErr = rc;
@@ -903,7 +1056,7 @@ uint8_t sf3d_ext_build_grid(const sf3d_grid_desc *g)
         gd.layerTab = (const uint16_t *)up(layerTab.data(), layerTab.size() * 2);
         gd.nSoilIds = nSoilIds;
         gd.freeRunoff = g->free_catchment_runoff; gd.freeLateral = g->free_lateral_drainage; gd.freeBottom = g->free_bottom_drainage;
-        gd.computeWater = S.water; gd.computeHeat = S.heat;
+        gd.computeWater = S.water; gd.computeHeat = S.heat; gd.heatSurfaceL1 = g->heat_surface_layer1;
         k_build_grid(S.eng.v, gd);
         dev_sync();
         for (void *d : tmp) dev_free(d);
@@ -912,9 +1065,27 @@ uint8_t sf3d_ext_build_grid(const sf3d_grid_desc *g)
         S.tab.dev_written(); S.bSlope.dev_written(); S.bSize.dev_written(); S.bRate.dev_written();
         S.bSum.dev_written(); S.bPresc.dev_written(); S.lidx.dev_written(); S.larea.dev_written();
         S.sink.dev_written(); S.pond.dev_written();
+        if (S.heat)
+        {
+            S.T.dev_written(); S.oldT.dev_written(); S.hSink.dev_written(); S.lfluxes.dev_written();
+            collect_heat_mirrors();
+            for (Mirror<double> *m : heat_boundary_mirrors) m->dev_written();
+        }
         S.topoDirty = true;
         return SF3D_OK;
     }, (uint8_t)SF3D_MEMORY_ERROR);
+}
+
+uint8_t sf3d_ext_set_fixed_temperature(uint32_t first, uint32_t count, const double *temperature, double depth)
+{
+    if (!temperature) return SF3D_PARAMETER_ERROR;
+    uint8_t firstErr = SF3D_OK;
+    for (uint32_t k = 0; k < count; ++k)
+    {
+        uint8_t rc = sf3d_set_node_boundary_fixed_temperature(first + k, temperature[k], depth);
+        if (rc && !firstErr) firstErr = rc;
+    }
+    return firstErr;
 }
 
 uint8_t sf3d_ext_get_counters(sf3d_counters *out)

@@ -36,9 +36,14 @@ uint32_t Engine::calcCurrentMaxIterationNumber(int approx) const
     return std::max(n, 25u);
 }
 
-// soilFluxes3D.cpp:1785-1821 (heat continuation: heat milestone)
+// soilFluxes3D.cpp:1785-1821
 double Engine::computeStep(double maxTimeStep)
 {
+    if (computeHeat)
+    {
+        k_reset_water_fluxes(v);            // resetFluxValues(false, true)
+        k_update_conductance(v);            // updateConductance()
+    }
     double dtWater;
     if (computeWater)
     {
@@ -47,8 +52,129 @@ double Engine::computeStep(double maxTimeStep)
     }
     else
         dtWater = std::min(maxTimeStep, p->deltaTmax);
+
+    if (computeHeat)
+    {
+        double dtHeat = dtWater;
+        k_save_water_fluxes(v, dtHeat, dtWater);
+        double dtHeatSum = 0.;
+        while (dtHeatSum < dtWater)
+        {
+            dtHeat = std::min(dtHeat, dtWater - dtHeatSum);
+            double reducedTimeStep;
+            while (!updateBoundaryHeatData(dtHeat, reducedTimeStep)) dtHeat = reducedTimeStep;
+            runHeat(dtHeat, dtWater);
+            dtHeatSum += dtHeat;
+        }
+    }
     ++cnt.steps;
     return dtWater;
+}
+
+// Heat::updateBoundaryHeatData, the time-step decision (heat.cpp:322-339)
+bool Engine::updateBoundaryHeatData(double maxTimeStep, double &actualTimeStep)
+{
+    k_boundary_heat(v, maxTimeStep);
+    Ctrl c{};
+    read_ctrl(v, &c);
+    const double courant = c.heatCourantMax;
+    const double minTimeStep = p->deltaTmin;
+    if (courant > 1. && maxTimeStep > minTimeStep)
+    {
+        actualTimeStep = std::max(minTimeStep, maxTimeStep / courant);
+        if (actualTimeStep > 1.) actualTimeStep = floor(actualTimeStep);
+        return false;
+    }
+    return true;
+}
+
+// CPUSolver::run, processType::Heat (cpusolver.cpp:77-91)
+void Engine::runHeat(double maxTimeStep, double dtWater)
+{
+    double dtHeat = maxTimeStep;
+    double sumHeatTime = 0;
+    while (sumHeatTime < maxTimeStep)
+    {
+        dtHeat = std::min(dtHeat, maxTimeStep - sumHeatTime);
+        if (!heatLoop(dtHeat, dtWater)) dtHeat *= 0.5;
+        else sumHeatTime += dtHeat;
+    }
+}
+
+// CPUSolver::heatLoop (cpusolver.cpp:471-605).  The linear solve is a Jacobi iteration with the
+// reference's infinity-norm stopping rule (the reference sweeps Gauss-Seidel sequentially,
+// heat.cpp:664-685: same fixed point); it may use up to 4x the reference's sweep
+// cap so that it reaches the tolerance whenever Gauss-Seidel does.
+bool Engine::heatLoop(double timeStepHeat, double timeStepWater)
+{
+    k_heat_begin(v, timeStepHeat, timeStepWater);       // reset heat fluxes ; x = T ; oldT = T ; C
+    k_heat_assemble(v, timeStepHeat, timeStepWater);
+
+    const int refCap = (int)calcCurrentMaxIterationNumber((int)p->maxApproximationsNumber - 1);
+    const int maxIter = 4 * refCap;
+    int launched = 0;
+    Ctrl c{};
+    int batch = 8;
+    for (;;)
+    {
+        const int n = std::min(batch, maxIter - launched);
+        for (int k = 0; k < n; ++k, ++launched)
+            k_heat_jacobi(v, xbuf(launched & 1), xbuf((launched + 1) & 1), maxIter, p->residualTolerance);
+        read_ctrl(v, &c);
+        if (c.status != SOLVE_RUNNING || launched >= maxIter) break;
+        batch = std::min(batch * 2, 64);
+    }
+    cnt.heat_sweeps += (uint64_t)c.sweeps;
+    const double *x = xbuf(c.sweeps & 1);
+
+    k_heat_post(v, x, timeStepHeat, timeStepWater, 0);  // T = x ; heat storage ; heat sink sum
+    read_ctrl(v, &c);
+    // Heat::evaluateHeatBalance (heat.cpp:373-390)
+    curStep.heatSinkSource = c.heatSinkSum;
+    curStep.heatStorage = c.heatStorage;
+    const double deltaHeatStorage = curStep.heatStorage - prevStep.heatStorage;
+    curStep.heatMBE = deltaHeatStorage - curStep.heatSinkSource;
+    const double referenceHeat = std::max(c.heatStorage * 1e-6, fabs(curStep.heatSinkSource));
+    curStep.heatMBR = curStep.heatMBE / referenceHeat;
+
+    if (fabs(curStep.heatMBR) > 1.0 && timeStepHeat > (p->deltaTmin * 10.0))
+    {
+        k_heat_copy_T(v, 1);                            // restore old temperatures
+        return false;
+    }
+    // Heat::updateHeatBalanceData (heat.cpp:393-398)
+    prevStep.heatStorage = curStep.heatStorage;
+    prevStep.heatSinkSource = curStep.heatSinkSource;
+    curPeriod.heatSinkSource += curStep.heatSinkSource;
+    k_heat_accept(v, timeStepHeat, timeStepWater);      // saveHeatFluxValues
+    k_heat_copy_T(v, 0);                                // oldT = T
+    ++cnt.heat_steps;
+    return true;
+}
+
+// Heat::initializeHeatBalance (heat.cpp:31-53)
+uint8_t Engine::initializeHeatBalance()
+{
+    wholePeriod.heatSinkSource = curPeriod.heatSinkSource = curStep.heatSinkSource = prevStep.heatSinkSource = 0.;
+    wholePeriod.heatMBE = curPeriod.heatMBE = curStep.heatMBE = 0.;
+    k_heat_post(v, nullptr, 1., 1., 2);
+    Ctrl c{};
+    read_ctrl(v, &c);
+    wholePeriod.heatStorage = curPeriod.heatStorage = curStep.heatStorage = prevStep.heatStorage = c.heatStorage;
+    return SF3D_OK;
+}
+
+// Heat::updateHeatBalanceDataWholePeriod (heat.cpp:400-413)
+void Engine::updateHeatBalanceDataWholePeriod()
+{
+    wholePeriod.heatSinkSource += curPeriod.heatSinkSource;
+    const double deltaStoragePeriod = curStep.heatStorage - curPeriod.heatStorage;
+    const double deltaStorageHistorical = curStep.heatStorage - wholePeriod.heatStorage;
+    curPeriod.heatMBE = deltaStoragePeriod - curPeriod.heatSinkSource;
+    wholePeriod.heatMBE = deltaStorageHistorical - wholePeriod.heatSinkSource;
+    const double referenceHeat = std::max(1., fabs(wholePeriod.heatSinkSource));
+    wholePeriod.heatMBR = wholePeriod.heatMBE / referenceHeat;
+    curPeriod.heatStorage = curStep.heatStorage;
 }
 
 // soilFluxes3D.cpp:1760-1777
@@ -60,6 +186,7 @@ void Engine::computePeriod(double timePeriod)
     while (sumCurrentTime < timePeriod)
         sumCurrentTime += computeStep(timePeriod - sumCurrentTime);
     if (computeWater) updateWaterBalanceDataWholePeriod();
+    if (computeHeat) updateHeatBalanceDataWholePeriod();
 }
 
 // CPUSolver::waterMainLoop (cpusolver.cpp:143-190)
@@ -72,6 +199,7 @@ bool Engine::waterMainLoop(double maxTimeStep, double &acceptedTimeStep)
         k_begin_try(v);                 // oldH = H ; x = H ; Se ; surface capacity
         xcur = 0;
         ++cnt.tries;
+        if (computeHeat) k_update_conductance(v);       // cpusolver.cpp:171-173
 
         stepStatus = waterApproximationLoop(acceptedTimeStep);
 

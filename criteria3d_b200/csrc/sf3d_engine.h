@@ -27,6 +27,7 @@ struct Engine {
     int xcur = 0;                           // which of x0/x1 holds the current solution vector
     int lastSweeps = 6;                     // sweeps of the previous solve (launch batching hint)
     bool computeWater = true;
+    bool computeHeat = false;
 
     double *xbuf(int k) const { return k ? v.x1 : v.x0; }
 
@@ -47,6 +48,13 @@ struct Engine {
     double        totalBoundaryWaterFlow(uint32_t boundaryType);
     uint8_t       initializeWaterBalance();
     void          updateWaterBalanceDataWholePeriod();
+
+    // heat (soilFluxes3D.cpp:1800-1818, cpusolver.cpp:77-91, 471-605, heat.cpp:237-413)
+    bool    updateBoundaryHeatData(double maxTimeStep, double &actualTimeStep);
+    void    runHeat(double maxTimeStep, double dtWater);
+    bool    heatLoop(double timeStepHeat, double timeStepWater);
+    uint8_t initializeHeatBalance();
+    void    updateHeatBalanceDataWholePeriod();
 
     uint32_t calcCurrentMaxIterationNumber(int approx) const;   // solver.h:55-59
 };

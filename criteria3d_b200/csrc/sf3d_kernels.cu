@@ -528,11 +528,18 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_build_grid(SF3DView v, GridDe
             if (layer == g.layers - 1) { if (g.freeBottom) { bt = BT_FREE_DRAINAGE; bSlope = 0.; bSize = (double)(float)area; } }
             else if (outlet && g.freeLateral) { bt = BT_FREE_LATERAL; bSlope = bSlopeF; bSize = (double)lateralArea; }
             else if (layer == 1 && g.boundaryL1) bt = g.boundaryL1[cell];
+            if (layer == 1 && g.heatSurfaceL1) { bt = BT_HEAT_SURFACE; bSlope = bSlopeF; bSize = area; }
         }
         if (bt != BT_NONE)          // setNodeBoundary (soilFluxes3D.cpp:689-725)
         {
             v.bSlope[i] = bSlope; v.bSize[i] = bSize;
             v.bRate[i] = 0.; v.bSum[i] = 0.; v.bPresc[i] = SF3D_NODATA;
+            if (g.computeHeat)          // soilFluxes3D.cpp:705-722
+            {
+                v.hbHeightWind[i] = v.hbHeightT[i] = v.hbRough[i] = v.hbAero[i] = v.hbSoilCond[i] = SF3D_NODATA;
+                v.hbT[i] = v.hbRH[i] = v.hbWind[i] = v.hbNetIrr[i] = v.hbFixT[i] = v.hbFixDepth[i] = SF3D_NODATA;
+                v.hbRad[i] = v.hbLat[i] = v.hbSens[i] = v.hbAdv[i] = 0.;
+            }
         }
         v.sink[i] = 0.;
 
@@ -563,6 +570,13 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_build_grid(SF3DView v, GridDe
             ++nLat;
         }
         v.meta[i] = bt | ((surface ? 1u : 0u) << 4) | (nLat << 5) | (mask << 9);
+        if (g.computeHeat)              // setNodeLink, soilFluxes3D.cpp:669-678
+            for (uint32_t sl = 0; sl < SF3D_NLINK; ++sl)
+                if ((mask >> sl) & 1u)
+                {
+                    v.lfluxes[(size_t)sl * N + i] = SF3D_NODATA;
+                    if (v.hfSaveMode == 2) for (int t = 1; t < 9; ++t) v.lfluxes[((size_t)t * SF3D_NLINK + sl) * N + i] = SF3D_NODATA;
+                }
 
         if (surface)
         {
@@ -573,9 +587,147 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_build_grid(SF3DView v, GridDe
         {
             const uint32_t sid = g.soilId ? g.soilId[cell] : 0;
             v.tab[i] = g.layerTab[(size_t)layer * g.nSoilIds + sid];
-            if (g.computeHeat) { v.T[i] = 293.15; v.oldT[i] = 293.15; v.hFlux[i] = 0.; v.hSink[i] = 0.; }
+            if (g.computeHeat) { v.T[i] = 273.15 + 20; v.oldT[i] = 273.15 + 20; v.hFlux[i] = 0.; v.hSink[i] = 0.; }
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// coupled heat (Heat::*, CPUSolver::heatLoop)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SF3D_BLOCK) kern_update_conductance(SF3DView v)
+{
+    for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
+        sf3d_row_update_conductance(v, i);
+}
+__global__ void __launch_bounds__(SF3D_BLOCK) kern_save_water_fluxes(SF3DView v, double dtHeat, double dtWater)
+{
+    for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
+        sf3d_row_save_water_fluxes(v, i, dtHeat, dtWater);
+}
+// updateBoundaryHeatData: heat flux per node + max heat-boundary Courant (heat.cpp:237-340)
+__global__ void __launch_bounds__(SF3D_BLOCK) kern_boundary_heat(SF3DView v, double maxTimeStep)
+{
+    __shared__ double sh[SF3D_BLOCK / 32];
+    double courant = 0.;
+    for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
+    {
+        const double c = sf3d_row_boundary_heat(v, i, maxTimeStep);
+        if (!(v.world > 1 && META_GHOST(v.meta[i]))) courant = (courant < c) ? c : courant;
+    }
+    courant = block_reduce<true>(courant, sh);
+    if (threadIdx.x == 0) v.partA[blockIdx.x] = courant;
+    if (last_block(v.ctrl))
+    {
+        const double cmax = fold_partials<true>(v.partA, sh);
+        if (threadIdx.x == 0) { v.ctrl->heatCourantMax = cmax; v.ctrl->red[0] = cmax; v.ctrl->ticket = 0; }
+    }
+}
+__global__ void kern_rule_heat_courant(Ctrl *c) { c->heatCourantMax = c->red[0]; }
+__global__ void __launch_bounds__(SF3D_BLOCK) kern_heat_begin(SF3DView v, double dtHeat, double dtWater)
+{
+    const size_t N = v.N;
+    for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
+    {
+        sf3d_row_heat_begin(v, i, dtHeat, dtWater);
+        // resetFluxValues(true, false) (heat.cpp:55-78)
+        if (v.hfSaveMode == 1) { for (int s = 0; s < SF3D_NLINK; ++s) v.lfluxes[(size_t)s * N + i] = SF3D_NODATA; }
+        else if (v.hfSaveMode == 2)
+            for (int t = 0; t < 5; ++t) for (int s = 0; s < SF3D_NLINK; ++s) v.lfluxes[((size_t)t * SF3D_NLINK + s) * N + i] = SF3D_NODATA;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+    { Ctrl *c = v.ctrl; c->status = SOLVE_RUNNING; c->sweeps = 0; c->lastNorm = 0.; }
+}
+__global__ void __launch_bounds__(SF3D_BLOCK) kern_heat_assemble(SF3DView v, double dtHeat, double dtWater)
+{
+    for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
+        if (!(v.world > 1 && META_GHOST(v.meta[i]))) sf3d_row_heat_assemble(v, i, dtHeat, dtWater);
+}
+__device__ __forceinline__ void rule_heat_jacobi(Ctrl *c, double norm, int maxIter, double tol)
+{
+    c->lastNorm = norm;
+    c->sweeps += 1;
+    if (norm < tol) c->status = SOLVE_CONVERGED;              // cpusolver.cpp:692 (no divergence test for heat)
+    else if (c->sweeps >= maxIter) c->status = SOLVE_MAXITER;
+}
+__global__ void kern_rule_heat_jacobi(Ctrl *c, int maxIter, double tol)
+{
+    if (c->status != SOLVE_RUNNING) return;
+    rule_heat_jacobi(c, c->red[0], maxIter, tol);
+}
+__global__ void __launch_bounds__(SF3D_BLOCK) kern_heat_jacobi(SF3DView v, const double *__restrict__ xin,
+                                                               double *__restrict__ xout, int maxIter, double tol)
+{
+    if (v.ctrl->status != SOLVE_RUNNING) return;
+    __shared__ double sh[SF3D_BLOCK / 32];
+    double norm = 0.;
+    for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
+    {
+        if (v.world > 1 && META_GHOST(v.meta[i])) continue;
+        const double d = sf3d_row_heat_jacobi(v, i, xin, xout);
+        norm = (norm < d) ? d : norm;
+    }
+    norm = block_reduce<true>(norm, sh);
+    if (threadIdx.x == 0) v.partA[blockIdx.x] = norm;
+    if (last_block(v.ctrl))
+    {
+        const double total = fold_partials<true>(v.partA, sh);
+        if (threadIdx.x == 0)
+        {
+            if (v.world == 1) rule_heat_jacobi(v.ctrl, total, maxIter, tol);
+            else v.ctrl->red[0] = total;
+            v.ctrl->ticket = 0;
+        }
+    }
+}
+__global__ void __launch_bounds__(SF3D_BLOCK) kern_heat_post(SF3DView v, const double *__restrict__ x, double dtHeat,
+                                                             double dtWater, int mode)
+{
+    __shared__ double sh[SF3D_BLOCK / 32];
+    double storage = 0., sinkSum = 0.;
+    for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
+    {
+        double s, q;
+        sf3d_row_heat_post(v, i, x, dtHeat, dtWater, mode, &s, &q);
+        if (v.world > 1 && META_GHOST(v.meta[i])) continue;
+        storage += s; sinkSum += q;
+    }
+    storage = block_reduce<false>(storage, sh);
+    sinkSum = block_reduce<false>(sinkSum, sh);
+    if (threadIdx.x == 0) { v.partA[blockIdx.x] = storage; v.partB[blockIdx.x] = sinkSum; }
+    if (last_block(v.ctrl))
+    {
+        const double st = fold_partials<false>(v.partA, sh);
+        const double sk = fold_partials<false>(v.partB, sh);
+        if (threadIdx.x == 0)
+        {
+            if (v.world == 1) { v.ctrl->heatStorage = st; v.ctrl->heatSinkSum = sk; }
+            else { v.ctrl->red[0] = st; v.ctrl->red[1] = sk; }
+            v.ctrl->ticket = 0;
+        }
+    }
+}
+__global__ void kern_rule_heat_post(Ctrl *c) { c->heatStorage = c->red[0]; c->heatSinkSum = c->red[1]; }
+__global__ void __launch_bounds__(SF3D_BLOCK) kern_heat_accept(SF3DView v, double dtHeat, double dtWater)
+{
+    for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
+        if (!(v.world > 1 && META_GHOST(v.meta[i]))) sf3d_row_heat_accept(v, i, dtHeat, dtWater);
+}
+// mode 0: oldT = T (accepted, cpusolver.cpp:598-602); mode 1: T = oldT (refused, :582-588)
+__global__ void __launch_bounds__(SF3D_BLOCK) kern_heat_copy_T(SF3DView v, int mode)
+{
+    for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
+    {
+        if (i < v.Ns) continue;
+        if (mode == 0) v.oldT[i] = v.T[i]; else v.T[i] = v.oldT[i];
+    }
+}
+// resetFluxValues(false, true): water flux snapshots to NODATA in save mode All (heat.cpp:80-93)
+__global__ void __launch_bounds__(SF3D_BLOCK) kern_reset_water_fluxes(SF3DView v)
+{
+    const size_t N = v.N;
+    for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
+        for (int t = 5; t < 9; ++t) for (int s = 0; s < SF3D_NLINK; ++s) v.lfluxes[((size_t)t * SF3D_NLINK + s) * N + i] = SF3D_NODATA;
 }
 
 __global__ void __launch_bounds__(SF3D_BLOCK) kern_count_links(SF3DView v, unsigned long long *out)
@@ -775,6 +927,42 @@ void k_build_grid(const SF3DView &v, const GridDev &g)
     kern_build_grid<<<reduce_blocks((uint32_t)(total > 0xFFFFFFFFull ? 0xFFFFFFFFull : total)), SF3D_BLOCK, 0, g_stream>>>(v, g);
     LAUNCH_CHECK();
 }
+
+void k_update_conductance(const SF3DView &v) { ProfScope ps(SF3D_K_OTHER); kern_update_conductance<<<GRID(v.N)>>>(v); LAUNCH_CHECK(); }
+void k_save_water_fluxes(const SF3DView &v, double dtHeat, double dtWater)
+{ ProfScope ps(SF3D_K_OTHER); kern_save_water_fluxes<<<GRID(v.N)>>>(v, dtHeat, dtWater); LAUNCH_CHECK(); }
+void k_reset_water_fluxes(const SF3DView &v) { if (v.hfSaveMode == 2) { kern_reset_water_fluxes<<<GRID(v.N)>>>(v); LAUNCH_CHECK(); } }
+void k_boundary_heat(const SF3DView &v, double maxTimeStep)
+{
+    ProfScope ps(SF3D_K_OTHER);
+    kern_boundary_heat<<<GRID(v.N)>>>(v, maxTimeStep); LAUNCH_CHECK();
+    if (v.world > 1) { comm_allreduce(v.ctrl->red, 1, true); kern_rule_heat_courant<<<1, 1, 0, g_stream>>>(v.ctrl); LAUNCH_CHECK(); }
+}
+void k_heat_begin(const SF3DView &v, double dtHeat, double dtWater)
+{ ProfScope ps(SF3D_K_OTHER); kern_heat_begin<<<GRID(v.N)>>>(v, dtHeat, dtWater); LAUNCH_CHECK(); }
+void k_heat_assemble(const SF3DView &v, double dtHeat, double dtWater)
+{ ProfScope ps(SF3D_K_OTHER); kern_heat_assemble<<<GRID(v.N)>>>(v, dtHeat, dtWater); LAUNCH_CHECK(); }
+void k_heat_jacobi(const SF3DView &v, const double *xin, double *xout, int maxIter, double tol)
+{
+    ProfScope ps(SF3D_K_OTHER);
+    kern_heat_jacobi<<<GRID(v.N)>>>(v, xin, xout, maxIter, tol); LAUNCH_CHECK();
+    if (v.world > 1)
+    {
+        comm_halo(xout);
+        comm_allreduce(v.ctrl->red, 1, true);
+        kern_rule_heat_jacobi<<<1, 1, 0, g_stream>>>(v.ctrl, maxIter, tol); LAUNCH_CHECK();
+    }
+}
+void k_heat_post(const SF3DView &v, const double *x, double dtHeat, double dtWater, int mode)
+{
+    ProfScope ps(SF3D_K_OTHER);
+    kern_heat_post<<<GRID(v.N)>>>(v, x, dtHeat, dtWater, mode); LAUNCH_CHECK();
+    if (v.world > 1) { comm_allreduce(v.ctrl->red, 2, false); kern_rule_heat_post<<<1, 1, 0, g_stream>>>(v.ctrl); LAUNCH_CHECK(); }
+}
+void k_heat_accept(const SF3DView &v, double dtHeat, double dtWater)
+{ ProfScope ps(SF3D_K_OTHER); kern_heat_accept<<<GRID(v.N)>>>(v, dtHeat, dtWater); LAUNCH_CHECK(); }
+void k_heat_copy_T(const SF3DView &v, int mode) { kern_heat_copy_T<<<GRID(v.N)>>>(v, mode); LAUNCH_CHECK(); }
+void k_halo(double *x) { comm_halo(x); }
 
 uint64_t k_count_links(const SF3DView &v)
 {

@@ -135,7 +135,7 @@ SF3D_HD void sf3d_row_restore_old(const SF3DView &v, uint32_t i) { v.H[i] = v.ol
 SF3D_HD double sf3d_heat_vapor_K(const SF3DView &v, uint32_t i);                       // soilPhysics.cpp:168-169
 SF3D_HD double sf3d_heat_dthetav_dh(const SF3DView &v, uint32_t i, double dThetadH);     // soilPhysics.cpp:287-299
 SF3D_HD double sf3d_heat_surface_boundary(const SF3DView &v, uint32_t i, double dt, double *upExtra);
-SF3D_HD double sf3d_heat_surface_pull(const SF3DView &v, uint32_t i, double dt, int *toBoundary);
+SF3D_HD double sf3d_heat_surface_pull(const SF3DView &v, uint32_t i, double dt, int *active);
 
 SF3D_HD double sf3d_culvert_flow(double waterLevel, double pond, double width, double height, double rough,
                                 double slope, double bSize)
@@ -200,16 +200,18 @@ SF3D_HD void sf3d_row_node_phase(const SF3DView &v, uint32_t i, double dt, int w
         const double maxSurfaceFlux = -hs * v.size[i] / dt;
         flow = sf3d_max(flow, maxSurfaceFlux);
     }
-    // pull formulation of the HeatSurface surface-water evaporation (water.cpp:722-736, Q9)
-    int evapToBoundary = 0;
+    // HeatSurface surface-water evaporation, pulled by the surface node through its Down link.
+    // The reference writes it from the soil node's iteration (water.cpp:722-736, order dependent
+    // under OpenMP); the sequential order is reproduced: applied after the node's own terms.
+    int evapActive = 0;
     double surfEvap = 0.;
-    if (surface && v.computeHeat && v.computeHeatVapor)
-        surfEvap = sf3d_heat_surface_pull(v, i, dt, &evapToBoundary);
+    if (surface && v.computeHeat && v.computeHeatVapor) surfEvap = sf3d_heat_surface_pull(v, i, dt, &evapActive);
 
     const uint32_t bt = META_BT(m);
     if (bt == BT_NONE)
     {
-        v.wFlow[i] = flow + surfEvap;       // surfEvap is 0 unless a HeatSurface node hangs below
+        if (evapActive) flow += surfEvap;                             // water.cpp:735
+        v.wFlow[i] = flow;
         return;
     }
 
@@ -266,11 +268,9 @@ SF3D_HD void sf3d_row_node_phase(const SF3DView &v, uint32_t i, double dt, int w
             rate = 0.;
             break;
     }
-    if (surface && evapToBoundary) rate = surfEvap;                   // water.cpp:732-733 overwrites
-    else flow += surfEvap;
-
     if (fabs(rate) < DBL_EPSILON) rate = 0.;
     else flow += rate;
+    if (evapActive) rate = surfEvap;                                  // water.cpp:732-733: overwrites the rate only
     v.bRate[i] = rate;
     v.wFlow[i] = flow;
 }

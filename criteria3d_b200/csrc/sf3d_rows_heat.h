@@ -1,11 +1,646 @@
-// sf3d_rows_heat.h -- heat-coupling hooks of the water rows and the rows of the heat update.
-// (Filled in by the heat milestone; until then the hooks are neutral and the C ABI refuses
-//  isComputeHeat = true with SF3D_PARAMETER_ERROR, so nothing silently runs without them.)
+// sf3d_rows_heat.h -- coupled heat transport: the closures of agrolib/soilFluxes3D/heat.cpp as
+// __host__ __device__ functions, the heat-coupling hooks of the water rows (vapour conductivity,
+// thermal liquid/vapour fluxes, HeatSurface evaporation) and the rows of the heat update itself.
+// Every function cites the reference lines it replaces; operation order follows the reference.
 #pragma once
 #include "sf3d_rows.h"
 
-SF3D_HD double sf3d_heat_vapor_K(const SF3DView &, uint32_t) { return 0.; }
-SF3D_HD double sf3d_heat_dthetav_dh(const SF3DView &, uint32_t, double) { return 0.; }
-SF3D_HD double sf3d_heat_surface_boundary(const SF3DView &, uint32_t, double, double *) { return 0.; }
-SF3D_HD double sf3d_heat_surface_pull(const SF3DView &, uint32_t, double, int *) { return 0.; }
-SF3D_HD double sf3d_heat_thermal_invariant(const SF3DView &, uint32_t, int, uint32_t) { return 0.; }
+// commonConstants.h
+#define HC_GRAVITY 9.80665
+#define HC_WATER_DENSITY 1000.
+#define HC_MH2O 0.018
+#define HC_ZEROCELSIUS 273.15
+#define HC_R_GAS 8.31447215
+#define HC_R_DRY_AIR 287.058
+#define HC_LAPSE_RATE_MOIST_AIR 0.0065
+#define HC_P0 101325.
+#define HC_TP0 293.16
+#define HC_GAMMA0 71.89
+#define HC_MINERAL_HK 2.5
+#define HC_VON_KARMAN 0.41
+#define HC_QUARTZ_DENSITY 2.648
+#define HC_HEAT_CAPACITY_WATER 4182000.
+#define HC_HEAT_CAPACITY_AIR 1290.
+#define HC_HEAT_CAPACITY_MINERAL 231000.
+#define HC_HEAT_CAPACITY_WATER_VAPOR 1996.
+#define HC_HEAT_CAPACITY_AIR_MOLAR 29.31
+#define HC_VAPOR_DIFFUSIVITY0 0.0000212
+#define HC_THETAMIN 0.15
+
+// ---- small closures (heat.cpp:1043-1250) ----------------------------------------------------
+SF3D_HD double h_latent_vaporization(double Tc) { return (2501000. - 2369.2 * Tc); }                    // :1085
+SF3D_HD double h_sat_vapor_pressure(double Tc) { return 611 * exp(17.502 * Tc / (Tc + 240.97)); }       // :1164
+SF3D_HD double h_vapor_conc_from_pressure(double p, double T) { return (p * HC_MH2O / (HC_R_GAS * T)); }   // :1219
+SF3D_HD double h_vapor_pressure_from_conc(double c, double T) { return (c * HC_R_GAS * T / HC_MH2O); }     // :1208
+SF3D_HD double h_soil_relative_humidity(double h, double T) { return exp(HC_MH2O * h * HC_GRAVITY / (HC_R_GAS * T)); }   // :1144
+SF3D_HD double h_vapor_from_psi_temp(double h, double T)                                                 // :1071
+{
+    const double svp = h_sat_vapor_pressure(T - HC_ZEROCELSIUS);
+    const double svc = h_vapor_conc_from_pressure(svp, T);
+    const double rh = h_soil_relative_humidity(h, T);
+    return svc * rh;
+}
+SF3D_HD double h_pressure_from_altitude(double height)                                                    // :1117
+{ return HC_P0 * pow(1 + height * HC_LAPSE_RATE_MOIST_AIR / HC_TP0, -HC_GRAVITY / (HC_LAPSE_RATE_MOIST_AIR * HC_R_DRY_AIR)); }
+SF3D_HD double h_air_molar_density(double p, double T) { return 44.65 * (p / HC_P0) * (HC_ZEROCELSIUS / T); }   // :1186
+SF3D_HD double h_air_vol_specific_heat(double p, double T) { return HC_HEAT_CAPACITY_AIR_MOLAR * h_air_molar_density(p, T); }   // :1197
+SF3D_HD double h_svp_slope(double Tc, double svp) { return (4098. * svp / ((237.3 + Tc) * (237.3 + Tc))); }   // :1175
+SF3D_HD double h_vapor_binary_diffusivity(double T) { return HC_VAPOR_DIFFUSIVITY0 * pow(T / HC_ZEROCELSIUS, 2.); }   // :1230
+SF3D_HD double h_soil_vapor_diffusivity(double thetaS, double theta, double T)                            // :1127
+{
+    const double beta = 0.66, m = 1.;
+    return h_vapor_binary_diffusivity(T) * beta * pow(thetaS - theta, m);
+}
+SF3D_HD double h_soil_surface_resistance(double thetaTop) { return 10 * exp(0.3563 * (HC_THETAMIN - thetaTop) * 100); }   // :1154
+SF3D_HD double h_water_return_flow_factor(double theta, double T, double clay)                            // :1097
+{
+    const double wc0 = 0.078 + 0.33 * clay;
+    if (theta < 0.01 * wc0) return 0.;
+    const double q0 = 2.52 + 7.25 * clay;
+    const double q = q0 * pow(T / 303., 2.);
+    return 1. / (1. + pow(theta / wc0, -q));
+}
+SF3D_HD double h_thermal_liquid_conductivity(double Tc, double h, double ILK)                             // :1242
+{
+    const double Gwt = 4.;
+    const double dGammadT = -0.1425 - 0.000576 * Tc;
+    return sf3d_max(0., ILK * h * Gwt * dGammadT / HC_GAMMA0);
+}
+SF3D_HD double h_particle_density(double om)                                                              // :1057
+{
+    if (om == SF3D_NODATA) om = 0.02;
+    return 1. / ((1. - om) / HC_QUARTZ_DENSITY + om / 1.43);
+}
+SF3D_HD double h_bulk_density(const SoilRec &s) { return (1. - s.thetaS) * h_particle_density(s.organicMatter); }   // :1043
+
+// ---- node closures ------------------------------------------------------------------------------
+SF3D_HD const SoilRec &h_soil(const SF3DView &v, uint32_t i) { return v.soil[v.tab[i]]; }
+SF3D_HD double h_theta(const SF3DView &v, uint32_t i, double signedPsi)            // computeNodeTheta_fromSignedPsi
+{ return (i < v.Ns) ? 1. : sf3d_theta_from_signed_psi(h_soil(v, i), v.wrcModel, signedPsi); }
+SF3D_HD double h_mean_T(const SF3DView &v, uint32_t i) { return (v.T[i] + v.oldT[i]) * 0.5; }   // getNodeMeanTemperature, soilPhysics.cpp:305-311
+
+// computeNodeThermalVaporConductivity (heat.cpp:780-819)
+SF3D_HD double h_thermal_vapor_conductivity(const SF3DView &v, uint32_t i, double T, double h)
+{
+    const SoilRec &s = h_soil(v, i);
+    const double Tc = T - HC_ZEROCELSIUS;
+    const double aPressure = h_pressure_from_altitude(v.z[i]);
+    const double theta = h_theta(v, i, h);
+    const double vDiff = h_soil_vapor_diffusivity(s.thetaS, theta, T);
+    const double svPressure = h_sat_vapor_pressure(Tc);
+    const double svpSlope = h_svp_slope(Tc, svPressure / 1000);
+    const double svcSlope = svpSlope * HC_MH2O * h_air_molar_density(aPressure, T) / aPressure;
+    const double vConc = h_vapor_from_psi_temp(h, T);
+    const double vPressure = h_vapor_pressure_from_conc(vConc, T);
+    const double rH = vPressure / svPressure;
+    const double satDegree = theta / s.thetaS;
+    const double eta = 9.5 + 3. * satDegree - 8.5 * exp(-pow((1. + 2.6 / sqrt(s.clay)) * satDegree, 4));
+    return eta * vDiff * svcSlope * rH;
+}
+// computeNodeIsothermalVaporConductivity (heat.cpp:827-841)
+SF3D_HD double h_isothermal_vapor_conductivity(const SF3DView &v, uint32_t i, double T, double h)
+{
+    const SoilRec &s = h_soil(v, i);
+    const double theta = h_theta(v, i, h);
+    const double vDiff = h_soil_vapor_diffusivity(s.thetaS, theta, T);
+    const double vConc = h_vapor_from_psi_temp(h, T);
+    return (vDiff * vConc * HC_MH2O) / (HC_R_GAS * T);
+}
+// computeNodeHeatAirConductivity (heat.cpp:752-772); computeWater is always true on this path
+SF3D_HD double h_air_conductivity(const SF3DView &v, uint32_t i, double T, double h)
+{
+    const double Tc = T - HC_ZEROCELSIUS;
+    double aK = 0.024 + 0.0000773 * Tc - 0.000000026 * Tc * Tc;
+    const double lambda = h_latent_vaporization(Tc);
+    const double niVK = h_thermal_vapor_conductivity(v, i, T, h);
+    aK += lambda * niVK;
+    return aK;
+}
+// computeNodeHeatSoilConductivity (heat.cpp:702-744)
+SF3D_HD double h_soil_heat_conductivity(const SF3DView &v, uint32_t i, double T, double h)
+{
+    const SoilRec &s = h_soil(v, i);
+    const double Tc = T - HC_ZEROCELSIUS;
+    const double wVol = h_theta(v, i, h);
+    const double sVol = 1. - s.thetaS;
+    const double aVol = s.thetaS - wVol;
+    const double wRet = h_water_return_flow_factor(wVol, T, s.clay);
+    const double wK = 0.554 + 0.0024 * Tc - 0.00000987 * Tc * Tc;
+    const double aK = h_air_conductivity(v, i, T, h);
+    const double fK = aK + wRet * (wK - aK);
+    const double ga = 0.088;
+    const double gc = 1. - 2. * ga;
+    const double aW = (2. / (1. + (aK / fK - 1.) * ga) + 1. / (1. + (aK / fK - 1.) * gc)) / 3.;
+    const double wW = (2. / (1. + (wK / fK - 1.) * ga) + 1. / (1. + (wK / fK - 1.) * gc)) / 3.;
+    const double sW = (2. / (1. + (HC_MINERAL_HK / fK - 1.) * ga) + 1. / (1. + (HC_MINERAL_HK / fK - 1.) * gc)) / 3.;
+    return (wVol * wW * wK + aVol * aW * aK + sVol * sW * HC_MINERAL_HK) / (wW * wVol + aW * aVol + sW * sVol);
+}
+// computeNodeVaporThetaV (heat.cpp:868-875)
+SF3D_HD double h_vapor_theta_v(const SF3DView &v, uint32_t i, double h, double T)
+{
+    const SoilRec &s = h_soil(v, i);
+    const double theta = h_theta(v, i, h);
+    return h_vapor_from_psi_temp(h, T) / HC_WATER_DENSITY * (s.thetaS - theta);
+}
+// computeNodeHeatCapacity (heat.cpp:849-860)
+SF3D_HD double h_heat_capacity(const SF3DView &v, uint32_t i, double h, double T)
+{
+    const double theta = h_theta(v, i, h);
+    double hc = (h_bulk_density(h_soil(v, i)) / HC_QUARTZ_DENSITY) * HC_HEAT_CAPACITY_MINERAL + theta * HC_HEAT_CAPACITY_WATER;
+    if (v.computeHeatVapor) hc += h_vapor_theta_v(v, i, h, T) * HC_HEAT_CAPACITY_AIR;
+    return hc;
+}
+// getNodeHeatStorage (soilFluxes3D.cpp:1545-1567)
+SF3D_HD double h_node_heat_storage(const SF3DView &v, uint32_t i, double h)
+{
+    const double T = v.T[i], size = v.size[i];
+    double heat = h_heat_capacity(v, i, h, T) * size * T;
+    if (v.computeHeatVapor) heat += h_vapor_theta_v(v, i, h, T) * h_latent_vaporization(T - HC_ZEROCELSIUS) * HC_WATER_DENSITY * size;
+    return heat;
+}
+// getNodeH_fromTimeSteps (heat.cpp:690-694)
+SF3D_HD double h_H_from_steps(const SF3DView &v, uint32_t i, double dtHeat, double dtWater)
+{
+    const double dH = v.H[i] - v.oldH[i];
+    return v.oldH[i] + dH * dtHeat / dtWater;
+}
+SF3D_HD double h_distance3d(const SF3DView &v, uint32_t i, uint32_t j)               // nodeDistance3D, soilPhysics.cpp:331-335
+{
+    const double dx = v.x[i] - v.x[j], dy = v.y[i] - v.y[j], dz = v.z[i] - v.z[j];
+    double n = 0; n += dx * dx; n += dy * dy; n += dz * dz;
+    return sqrt(n);
+}
+
+// ---- water-side hooks --------------------------------------------------------------------------
+// computeNodeK's vapour term (soilPhysics.cpp:168-169)
+SF3D_HD double sf3d_heat_vapor_K(const SF3DView &v, uint32_t i)
+{ return h_isothermal_vapor_conductivity(v, i, h_mean_T(v, i), v.H[i] - v.z[i]) * (HC_GRAVITY / HC_WATER_DENSITY); }
+
+// computeNodedThetaVdH (soilPhysics.cpp:287-299), temperature = node mean temperature (water.cpp:294)
+SF3D_HD double sf3d_heat_dthetav_dh(const SF3DView &v, uint32_t i, double dThetadH)
+{
+    const double T = h_mean_T(v, i);
+    const double h = v.H[i] - v.z[i];
+    const double rH = h_soil_relative_humidity(h, T);
+    const double satVP = h_sat_vapor_pressure(T - HC_ZEROCELSIUS);
+    const double satVC = h_vapor_conc_from_pressure(satVP, T);
+    const double theta = h_theta(v, i, h);
+    const double dThetaVdPsi = (satVC * rH / HC_WATER_DENSITY) * ((h_soil(v, i).thetaS - theta) * HC_MH2O / (HC_R_GAS * T) - dThetadH / HC_GRAVITY);
+    return dThetaVdPsi * HC_GRAVITY;
+}
+
+// computeThermalLiquidFlux / computeThermalVaporFlux (heat.cpp:458-553); forWater selects the
+// processType::Water branch (mean temperatures, current heads) or the Heat branch
+SF3D_HD void h_thermal_operands(const SF3DView &v, uint32_t i, uint32_t j, bool forWater, bool liquid, double dtHeat, double dtWater,
+                               double &srcT, double &dstT, double &srcH, double &dstH)
+{
+    if (forWater)
+    {
+        srcT = h_mean_T(v, i); dstT = h_mean_T(v, j);
+        srcH = v.H[i] - v.z[i]; dstH = v.H[j] - v.z[j];
+    }
+    else
+    {
+        srcT = v.T[i]; dstT = v.T[j];
+        if (!liquid || dtHeat != dtWater)
+        {
+            srcH = (h_H_from_steps(v, i, dtHeat, dtWater) + v.oldH[i]) * 0.5 - v.z[i];
+            dstH = (h_H_from_steps(v, j, dtHeat, dtWater) + v.oldH[j]) * 0.5 - v.z[j];
+        }
+        else
+        {
+            srcH = (v.H[i] + v.oldH[i]) * 0.5 - v.z[i];
+            dstH = (v.H[j] + v.oldH[j]) * 0.5 - v.z[j];
+        }
+    }
+}
+SF3D_HD double h_thermal_liquid_flux(const SF3DView &v, uint32_t i, int slot, uint32_t j, bool forWater, double dtHeat, double dtWater)
+{
+    double srcT, dstT, srcH, dstH;
+    h_thermal_operands(v, i, j, forWater, true, dtHeat, dtWater, srcT, dstT, srcH, dstH);
+    const double a = h_thermal_liquid_conductivity(srcT - HC_ZEROCELSIUS, srcH, v.K[i]);
+    const double b = h_thermal_liquid_conductivity(dstT - HC_ZEROCELSIUS, dstH, v.K[j]);
+    const double avg = sf3d_mean(a, b, 2);                        // computeMean default = Logarithmic
+    const double density = avg * (dstT - srcT) / h_distance3d(v, i, j);
+    return density * v.larea[(size_t)slot * v.N + i];
+}
+SF3D_HD double h_thermal_vapor_flux(const SF3DView &v, uint32_t i, int slot, uint32_t j, bool forWater, double dtHeat, double dtWater)
+{
+    double srcT, dstT, srcH, dstH;
+    h_thermal_operands(v, i, j, forWater, false, dtHeat, dtWater, srcT, dstT, srcH, dstH);
+    const double a = h_thermal_vapor_conductivity(v, i, srcT, srcH);
+    const double b = h_thermal_vapor_conductivity(v, j, dstT, dstH);
+    const double avg = sf3d_mean(a, b, 2);
+    const double density = avg * (dstT - srcT) / h_distance3d(v, i, j);
+    return density * v.larea[(size_t)slot * v.N + i];
+}
+// water.cpp:329-340: thermal liquid (+ vapour / rho_w) flux added to the row's invariant fluxes
+SF3D_HD double sf3d_heat_thermal_invariant(const SF3DView &v, uint32_t i, int slot, uint32_t j)
+{
+    double f = h_thermal_liquid_flux(v, i, slot, j, true, 0., 0.);
+    if (v.computeHeatVapor) f += h_thermal_vapor_flux(v, i, slot, j, true, 0., 0.) / HC_WATER_DENSITY;
+    return f;
+}
+
+// computeNodeAtmosphericLatentVaporFlux (heat.cpp:988-1007), node = HeatSurface soil node
+SF3D_HD double h_atmospheric_latent_vapor_flux(const SF3DView &v, uint32_t i)
+{
+    const uint32_t up = v.lidx[i];
+    if (!(up < v.Ns)) return 0.;
+    const double satP = h_sat_vapor_pressure(v.hbT[i] - HC_ZEROCELSIUS);
+    const double satC = h_vapor_conc_from_pressure(satP, v.hbT[i]);
+    const double boundaryVapor = satC * (v.hbRH[i] / 100.);
+    const double deltaVapor = boundaryVapor - h_vapor_from_psi_temp(v.H[i] - v.z[i], v.T[i]);     // getNodeVapor
+    const double total = 1. / ((1. / v.hbAero[i]) + (1. / v.hbSoilCond[i]));
+    return deltaVapor * total;
+}
+// computeNodeAtmosphericLatentSurfaceWaterFlux (heat.cpp:1013-1036), node = surface node, down = HeatSurface node
+SF3D_HD double h_atmospheric_surface_water_flux(const SF3DView &v, uint32_t down)
+{
+    const double satP = h_sat_vapor_pressure(v.hbT[down] - HC_ZEROCELSIUS);
+    const double satC = h_vapor_conc_from_pressure(satP, v.hbT[down]);
+    const double boundaryVapor = satC * (v.hbRH[down] / 100.);
+    const double deltaVapor = boundaryVapor - satC;
+    return deltaVapor * v.hbAero[down];
+}
+// getNodeSurfaceWaterFraction (soilPhysics.cpp:313-323)
+SF3D_HD double h_surface_water_fraction(const SF3DView &v, uint32_t s)
+{
+    if (!(s < v.Ns)) return 0.;
+    const double hV = sf3d_max(0., v.H[s] - v.z[s]);
+    const double h0 = sf3d_max(0.001, v.pond[s]);
+    return sf3d_min(1., hV / h0);
+}
+
+// HeatSurface branch of updateBoundaryWaterData (water.cpp:708-747), soil-node side: soil evaporation
+SF3D_HD double sf3d_heat_surface_boundary(const SF3DView &v, uint32_t i, double dt, double *)
+{
+    const uint32_t m = v.meta[i];
+    const bool upLinked = META_HAS_SLOT(m, 0);
+    const uint32_t up = upLinked ? v.lidx[i] : 0xFFFFFFFFu;
+    const double fraction = upLinked ? h_surface_water_fraction(v, up) : 0.;
+    const double area = v.larea[i];
+    double soilEvap = h_atmospheric_latent_vapor_flux(v, i) / HC_WATER_DENSITY * area;
+    if (fraction > 0.) soilEvap *= (1. - fraction);
+    const SoilRec &s = h_soil(v, i);
+    const double thetaV = sf3d_theta_from_se(s, v.Se[i]);
+    soilEvap = (soilEvap < 0.) ? sf3d_max(soilEvap, -(thetaV - s.thetaR) * v.size[i] / dt)
+                               : sf3d_min(soilEvap, (s.thetaS - s.thetaR) * v.size[i] / dt);
+    return soilEvap;
+}
+// the same branch, surface-node side (the reference writes the up node from the soil node's
+// iteration, water.cpp:722-736; here the surface node pulls it through its Down link: Q9).
+// Returns the surface-water evaporation [m3 s-1]; *active = 0 when nothing is to be applied.
+SF3D_HD double sf3d_heat_surface_pull(const SF3DView &v, uint32_t i, double dt, int *active)
+{
+    *active = 0;
+    const uint32_t m = v.meta[i];
+    if (!META_HAS_SLOT(m, 1)) return 0.;
+    const uint32_t down = v.lidx[(size_t)v.N + i];
+    if (META_BT(v.meta[down]) != BT_HEAT_SURFACE) return 0.;
+    if (!META_HAS_SLOT(v.meta[down], 0) || v.lidx[down] != i) return 0.;
+    const double fraction = h_surface_water_fraction(v, i);
+    if (!(fraction > 0.)) return 0.;
+    const double area = v.larea[down];                            // linkData[0].interfaceArea of the soil node
+    double surfEvap = h_atmospheric_surface_water_flux(v, down) / HC_WATER_DENSITY * area;
+    surfEvap *= fraction;
+    const double waterVolume = (v.H[i] - v.z[i]) * v.size[i];
+    surfEvap = sf3d_max(surfEvap, -waterVolume / dt);
+    *active = 1;
+    return surfEvap;
+}
+
+// ==========================================================================================
+// Heat::updateConductance per node (heat.cpp:214-235) with computeNodeAerodynamicConductance
+// (heat.cpp:882-951, fixed-point iteration, at most 100 rounds)
+// ==========================================================================================
+SF3D_HD double h_aerodynamic_conductance(const SF3DView &v, uint32_t i)
+{
+    const double heightT = v.hbHeightT[i], heightWind = v.hbHeightWind[i];
+    const double soilT = v.T[i], rHeight = v.hbRough[i], airT = v.hbT[i];
+    const double wind = sf3d_max(v.hbWind[i], 0.01);
+    const double zeroPlane = 0.77 * rHeight;
+    const double rMomentum = 0.13 * rHeight;
+    const double rHeat = 0.2 * rMomentum;
+    double psiM = 0., psiH = 0.;
+    const double cH = h_air_vol_specific_heat(h_pressure_from_altitude(heightWind), airT);
+    bool first = true;
+    double oldHf = SF3D_NODATA, K = SF3D_NODATA;
+    for (int counter = 0; counter < 100; ++counter)
+    {
+        const double uStar = HC_VON_KARMAN * wind / (log((heightWind - zeroPlane + rMomentum) / rMomentum) + psiM);
+        K = HC_VON_KARMAN * uStar / (log((heightT - zeroPlane + rHeat) / rHeat) + psiH);
+        const double Hf = K * cH * (soilT - airT);
+        const double sP = -HC_VON_KARMAN * heightWind * HC_GRAVITY * Hf / (cH * airT * (pow(uStar, 3)));
+        if (sP > 0) { psiH = 6 * log(1 + sP); psiM = psiH; }
+        else { psiH = -2 * log((1 + sqrt(1 - 16 * sP)) / 2); psiM = 0.6 * psiH; }
+        if (first) first = false;
+        else if (fabs(Hf - oldHf) < 0.01) break;
+        oldHf = Hf;
+    }
+    return K;
+}
+SF3D_HD void sf3d_row_update_conductance(const SF3DView &v, uint32_t i)
+{
+    if (META_BT(v.meta[i]) != BT_HEAT_SURFACE) return;
+    v.hbAero[i] = h_aerodynamic_conductance(v, i);
+    const double theta = h_theta(v, i, v.H[i] - v.z[i]);
+    v.hbSoilCond[i] = 1. / h_soil_surface_resistance(theta);
+}
+
+// ==========================================================================================
+// Heat::saveNodeWaterFluxes (heat.cpp:109-138): per link water / vapour flux snapshot, float-rounded
+// ==========================================================================================
+SF3D_HD double h_isothermal_vapor_flux(const SF3DView &v, uint32_t i, int slot, uint32_t j, double dtHeat, double dtWater)   // :561-582
+{
+    const double srcH = (h_H_from_steps(v, i, dtHeat, dtWater) + v.oldH[i]) * 0.5 - v.z[i];
+    const double dstH = (h_H_from_steps(v, j, dtHeat, dtWater) + v.oldH[j]) * 0.5 - v.z[j];
+    const double a = h_isothermal_vapor_conductivity(v, i, v.T[i], srcH);
+    const double b = h_isothermal_vapor_conductivity(v, j, v.T[j], dstH);
+    const double avg = sf3d_mean(a, b, 2);
+    const double srcPsi = srcH * HC_GRAVITY, dstPsi = dstH * HC_GRAVITY;
+    const double deltaPsi = dstPsi - srcPsi;
+    return avg * deltaPsi / h_distance3d(v, i, j) * v.larea[(size_t)slot * v.N + i];
+}
+SF3D_HD void sf3d_row_save_water_fluxes(const SF3DView &v, uint32_t i, double dtHeat, double dtWater)
+{
+    const size_t N = v.N;
+    const uint32_t m = v.meta[i];
+    #pragma unroll 1
+    for (int slot = 0; slot < SF3D_NLINK; ++slot)
+    {
+        if (!META_HAS_SLOT(m, slot)) continue;
+        const size_t li = (size_t)slot * N + i;
+        const uint32_t j = v.lidx[li];
+        const double srcAvgH = h_H_from_steps(v, i, dtHeat, dtWater);
+        const double dstAvgH = h_H_from_steps(v, j, dtHeat, dtWater);
+        const double A = v.mval[(size_t)sf3d_col_of_slot(slot) * N + i];      // normalised entry x 1.0 (Q1); 0 if not stored (Q2)
+        const double isoLiquid = A * (srcAvgH - dstAvgH);
+        const bool deep = !(i < v.Ns) && !(j < v.Ns);
+        const double isoVapor = deep ? h_isothermal_vapor_flux(v, i, slot, j, dtHeat, dtWater) : 0.;
+        const double thLiquid = deep ? h_thermal_liquid_flux(v, i, slot, j, false, dtHeat, dtWater) : 0.;
+        const double thVapor = deep ? h_thermal_vapor_flux(v, i, slot, j, false, dtHeat, dtWater) : 0.;
+        v.lwFlux[li] = (double)(float)(isoLiquid - isoVapor / HC_WATER_DENSITY + thLiquid);
+        v.lvFlux[li] = (double)(float)(isoVapor + thVapor);
+        if (v.hfSaveMode == 2)
+        {
+            v.lfluxes[(size_t)5 * SF3D_NLINK * N + li] = (double)(float)isoLiquid;
+            v.lfluxes[(size_t)6 * SF3D_NLINK * N + li] = (double)(float)thLiquid;
+            v.lfluxes[(size_t)7 * SF3D_NLINK * N + li] = (double)(float)isoVapor;
+            v.lfluxes[(size_t)8 * SF3D_NLINK * N + li] = (double)(float)thVapor;
+        }
+    }
+}
+
+// ==========================================================================================
+// Heat::updateBoundaryHeatData per node (heat.cpp:243-320); returns the node's Courant value
+// ==========================================================================================
+SF3D_HD double sf3d_row_boundary_heat(const SF3DView &v, uint32_t i, double maxTimeStep)
+{
+    if (i < v.Ns) return 0.;
+    double flux = v.hSink[i];
+    const uint32_t bt = META_BT(v.meta[i]);
+    double courant = 0.;
+    if (bt == BT_NONE) { v.hFlux[i] = flux; return 0.; }
+    const double upArea = v.larea[i];
+    if (bt == BT_HEAT_SURFACE)
+    {
+        double adv = 0., sens = 0., lat = 0., rad = 0.;
+        if (v.hbNetIrr[i] != SF3D_NODATA) rad = v.hbNetIrr[i];
+        // computeNodeAtmosphericSensibleHeatFlux (heat.cpp:957-968)
+        {
+            const uint32_t up = v.lidx[i];
+            if (up < v.Ns)
+            {
+                const double pressure = h_pressure_from_altitude(v.z[i]);
+                const double deltaT = v.hbT[i] - v.T[i];
+                sens += h_air_vol_specific_heat(pressure, v.hbT[i]) * deltaT * v.hbAero[i];
+            }
+        }
+        if (v.computeHeatVapor)
+        {
+            // computeNodeAtmosphericLatentHeatFlux (heat.cpp:974-982) / upLinkArea
+            const uint32_t up = v.lidx[i];
+            double latent = 0.;
+            if (up < v.Ns) latent = v.bRate[i] * HC_WATER_DENSITY * h_latent_vaporization(v.T[i] - HC_ZEROCELSIUS);
+            lat += latent / upArea;
+        }
+        if (v.computeHeatAdvection)
+        {
+            double advT = v.hbT[i];
+            const double wFlux = v.lwFlux[i];                       // Up link water flux
+            if (wFlux > 0.) adv = wFlux * HC_HEAT_CAPACITY_WATER * advT / upArea;
+            if (v.bRate[i] < 0.) advT = v.T[i];
+            adv += v.bRate[i] * HC_WATER_DENSITY * HC_HEAT_CAPACITY_WATER_VAPOR * advT / upArea;
+        }
+        v.hbAdv[i] = adv; v.hbSens[i] = sens; v.hbLat[i] = lat; v.hbRad[i] = rad;
+        flux += upArea * (rad + sens + lat + adv);
+        const double hc = h_heat_capacity(v, i, v.oldH[i], v.oldT[i]);      // (sic) oldPressureHead passed as h, heat.cpp:293
+        courant = fabs(flux) * maxTimeStep / (hc * v.size[i]);
+    }
+    else if (bt == BT_FREE_DRAINAGE || bt == BT_PRESCRIBED)
+    {
+        if (v.computeHeatAdvection)
+        {
+            const double wFlux = v.bRate[i];
+            const double advT = (wFlux < 0) ? v.T[i] : v.hbFixT[i];
+            const double adv = wFlux * HC_HEAT_CAPACITY_WATER * advT / upArea;
+            v.hbAdv[i] = adv;
+            flux += upArea * adv;
+        }
+        if (v.hbFixT[i] != SF3D_NODATA)
+        {
+            const double avgH = (v.H[i] + v.oldH[i]) * 0.5;
+            const double bK = h_soil_heat_conductivity(v, i, v.T[i], avgH - v.z[i]);
+            const double deltaT = v.hbFixT[i] - v.T[i];
+            flux += bK * deltaT / v.hbFixDepth[i] * upArea;
+        }
+    }
+    v.hFlux[i] = flux;
+    return courant;
+}
+
+// ==========================================================================================
+// CPUSolver::heatLoop, per-node pieces (cpusolver.cpp:471-605)
+// ==========================================================================================
+// x = T ; oldT = T ; C = heat capacity x volume  (:476-491)
+SF3D_HD void sf3d_row_heat_begin(const SF3DView &v, uint32_t i, double dtHeat, double dtWater)
+{
+    const double T = v.T[i];
+    v.x0[i] = T;
+    v.oldT[i] = T;
+    if (i < v.Ns) return;
+    const double nodeH = h_H_from_steps(v, i, dtHeat, dtWater);
+    const double avgH = (v.oldH[i] + nodeH) * 0.5 - v.z[i];
+    v.cap[i] = h_heat_capacity(v, i, avgH, T) * v.size[i];
+}
+
+// saveNodeHeatSpecificFlux (heat.cpp:198-212): float-rounded accumulation into HeatTotal
+SF3D_HD void h_save_specific_flux(const SF3DView &v, uint32_t i, int slot, int type, double value)
+{
+    if (v.hfSaveMode == 0) return;
+    const size_t N = v.N, li = (size_t)slot * N + i;
+    value = (double)(float)value;
+    double &total = v.lfluxes[li];                              // type 0 = HeatTotal
+    total = (double)(float)((total == SF3D_NODATA) ? value : total + value);
+    if (v.hfSaveMode == 2) v.lfluxes[(size_t)type * SF3D_NLINK * N + li] = value;
+}
+
+// Heat::conduction (heat.cpp:643-661)
+SF3D_HD double h_conduction(const SF3DView &v, uint32_t i, int slot, uint32_t j, double dtHeat, double dtWater)
+{
+    const double zeta = v.larea[(size_t)slot * v.N + i] / h_distance3d(v, i, j);
+    const double nodeAvgH = (h_H_from_steps(v, i, dtHeat, dtWater) + v.oldH[i]) * 0.5 - v.z[i];
+    const double linkAvgH = (h_H_from_steps(v, j, dtHeat, dtWater) + v.oldH[j]) * 0.5 - v.z[j];
+    const double nodeK = h_soil_heat_conductivity(v, i, v.T[i], nodeAvgH);
+    const double linkK = h_soil_heat_conductivity(v, j, v.T[j], linkAvgH);
+    return zeta * sf3d_mean(nodeK, linkK, 2);
+}
+// computeAdvectiveFlux (heat.cpp:606-621)
+SF3D_HD double h_advective_flux(const SF3DView &v, uint32_t i, int slot, uint32_t j)
+{
+    const size_t li = (size_t)slot * v.N + i;
+    const double lw = v.lwFlux[li];
+    const double lT = v.T[(lw < 0.) ? i : j];
+    const double vw = v.lvFlux[li];
+    const double vT = v.T[(vw < 0.) ? i : j];
+    return (HC_HEAT_CAPACITY_WATER * lw) * lT + (HC_HEAT_CAPACITY_WATER_VAPOR * vw) * vT;
+}
+
+// one row of the heat system (cpusolver.cpp:496-568).  Column order Up, Down, Lateral 0..7
+// (cpusolver.cpp:524-540); stored in SLOT order, which is the same order.
+SF3D_HD void sf3d_row_heat_assemble(const SF3DView &v, uint32_t i, double dtHeat, double dtWater)
+{
+    const size_t N = v.N;
+    if (i < v.Ns)
+    {
+        #pragma unroll 1
+        for (int s = 0; s < SF3D_NLINK; ++s) v.mval[(size_t)s * N + i] = 0.;
+        v.hdiag[i] = 0.;
+        v.b[i] = v.T[i];
+        return;
+    }
+    const uint32_t m = v.meta[i];
+    const double nodeT = v.T[i];
+    const double nodeH = h_H_from_steps(v, i, dtHeat, dtWater);
+    const double oldPsi = v.oldH[i] - v.z[i];
+    const SoilRec &s = h_soil(v, i);
+    const double dTheta = sf3d_theta_from_signed_psi(s, v.wrcModel, nodeH - v.z[i]) - sf3d_theta_from_signed_psi(s, v.wrcModel, oldPsi);
+    double heatCapacity = dTheta * HC_HEAT_CAPACITY_WATER * nodeT;
+    if (v.computeHeatVapor)
+    {
+        const double dThetaV = h_vapor_theta_v(v, i, nodeH - v.z[i], nodeT) - h_vapor_theta_v(v, i, oldPsi, v.oldT[i]);
+        heatCapacity += dThetaV * HC_HEAT_CAPACITY_AIR * nodeT;
+        heatCapacity += dThetaV * h_latent_vaporization(nodeT - HC_ZEROCELSIUS) * HC_WATER_DENSITY;
+    }
+    heatCapacity *= v.size[i];
+
+    const double wf = v.heatWF;
+    double sumDP = 0., sumF0 = 0., invariant = 0.;
+    double val[SF3D_NLINK];
+    #pragma unroll 1
+    for (int slot = 0; slot < SF3D_NLINK; ++slot)
+    {
+        val[slot] = 0.;
+        if (!META_HAS_SLOT(m, slot)) continue;
+        const uint32_t j = v.lidx[(size_t)slot * N + i];
+        if (j < v.Ns) continue;                                    // !isHeatNode(linked), heat.cpp:423
+        const double e = h_conduction(v, i, slot, j, dtHeat, dtWater);
+        double latent = 0., advective = 0.;
+        if (v.computeHeatVapor)
+        {
+            // computeIsothermalLatentHeatFlux (heat.cpp:590-600)
+            const double avgLambda = (h_latent_vaporization(v.T[i] - HC_ZEROCELSIUS) + h_latent_vaporization(v.T[j] - HC_ZEROCELSIUS)) * 0.5;
+            latent = avgLambda * h_isothermal_vapor_flux(v, i, slot, j, dtHeat, dtWater);
+            h_save_specific_flux(v, i, slot, 2, latent);
+        }
+        if (v.computeHeatAdvection)
+        {
+            advective = h_advective_flux(v, i, slot, j);
+            h_save_specific_flux(v, i, slot, 4, advective);
+        }
+        invariant += advective + latent;
+        // cpusolver.cpp:545-552
+        sumDP += e * wf;
+        const double dT0 = v.oldT[j] - v.oldT[i];
+        sumF0 += e * (1. - wf) * dT0;
+        val[slot] = e * (-wf);
+    }
+    const double capOverDt = v.cap[i] / dtHeat;
+    const double diag = sumDP + capOverDt;
+    double b = v.cap[i] * v.oldT[i] / dtHeat - heatCapacity / dtHeat + v.hFlux[i] + invariant + sumF0;
+    if (diag > 0)
+    {
+        b /= diag;
+        #pragma unroll 1
+        for (int slot = 0; slot < SF3D_NLINK; ++slot) val[slot] /= diag;
+    }
+    #pragma unroll 1
+    for (int slot = 0; slot < SF3D_NLINK; ++slot) v.mval[(size_t)slot * N + i] = val[slot];
+    v.hdiag[i] = diag;
+    v.b[i] = b;
+}
+
+// one Jacobi row of the heat system; returns |dx| (the reference sweeps Gauss-Seidel in place with
+// the same row formula and an infinity norm, heat.cpp:664-685)
+SF3D_HD double sf3d_row_heat_jacobi(const SF3DView &v, uint32_t i, const double *__restrict__ xin, double *__restrict__ xout)
+{
+    const size_t N = v.N;
+    const double xold = xin[i];
+    if (i < v.Ns || v.hdiag[i] == 0.) { xout[i] = xold; return 0.; }
+    const uint32_t m = v.meta[i];
+    double xnew = v.b[i];
+    #pragma unroll
+    for (int slot = 0; slot < SF3D_NLINK; ++slot)
+    {
+        const double A = v.mval[(size_t)slot * N + i];
+        const uint32_t j = META_HAS_SLOT(m, slot) ? v.lidx[(size_t)slot * N + i] : i;
+        xnew -= A * xin[j];
+    }
+    xout[i] = xnew;
+    return fabs(xnew - xold);
+}
+
+// T = x ; heat storage and sink sums (cpusolver.cpp:573-577, heat.cpp:342-370)
+SF3D_HD void sf3d_row_heat_post(const SF3DView &v, uint32_t i, const double *__restrict__ x, double dtHeat, double dtWater,
+                               int mode, double *storage, double *sinkSum)
+{
+    *storage = 0.; *sinkSum = 0.;
+    if (i < v.Ns) return;
+    if (mode == 0) v.T[i] = x[i];
+    const double nodeH = (mode == 2) ? v.H[i] : h_H_from_steps(v, i, dtHeat, dtWater);
+    *storage = h_node_heat_storage(v, i, nodeH - v.z[i]);
+    const double f = v.hFlux[i];
+    *sinkSum = (f != 0.) ? f * dtHeat : 0.;
+}
+
+// saveNodeHeatFluxes (heat.cpp:160-196) + oldT = T (cpusolver.cpp:598-602)
+SF3D_HD void sf3d_row_heat_accept(const SF3DView &v, uint32_t i, double dtHeat, double dtWater)
+{
+    if (i < v.Ns) return;
+    const size_t N = v.N;
+    if (v.hfSaveMode != 0)
+    {
+        const uint32_t m = v.meta[i];
+        #pragma unroll 1
+        for (int slot = 0; slot < SF3D_NLINK; ++slot)
+        {
+            if (!META_HAS_SLOT(m, slot)) continue;
+            const uint32_t j = v.lidx[(size_t)slot * N + i];
+            if (j < v.Ns) continue;
+            const double mv = v.mval[(size_t)slot * N + i] * v.hdiag[i];     // getMatrixElement: value x diagonal (kept for heat)
+            double heatDiff = mv * (v.T[i] - v.T[j]) * v.heatWF + mv * (v.oldT[i] - v.oldT[j]) * (1. - v.heatWF);
+            if (v.hfSaveMode == 1) h_save_specific_flux(v, i, slot, 0, heatDiff);
+            else
+            {
+                if (v.computeHeatVapor)
+                {
+                    const double thLatent = h_thermal_vapor_flux(v, i, slot, j, false, dtHeat, dtWater) * h_latent_vaporization(v.T[i] - HC_ZEROCELSIUS);
+                    h_save_specific_flux(v, i, slot, 3, thLatent);
+                    heatDiff -= thLatent;
+                }
+                h_save_specific_flux(v, i, slot, 1, heatDiff);
+            }
+        }
+    }
+}

@@ -171,6 +171,7 @@ class Catchment:
         d.layer_horizon = self.layer_horizon.ctypes.data_as(C.POINTER(C.c_uint16))
         d.boundary_l1 = None
         d.free_catchment_runoff = d.free_lateral_drainage = d.free_bottom_drainage = 1
+        d.heat_surface_layer1 = 1 if self.heat else 0
         return d
 
     # ---- forcing ---------------------------------------------------------------------
@@ -212,7 +213,36 @@ def setup(sf: SoilFluxes3D, cat: Catchment, threads: int = 0,
     _ok(sf.setNumericalParameters(*numerics), "setNumericalParameters")
     sf.setThreadsNumber(threads)
     _ok(sf.set_field(Field.MATRIC_POTENTIAL, 0, cat.initial_matric_potential()), "initial matric potential")
+    if cat.heat:
+        setup_heat(sf, cat)
     _ok(sf.initializeBalance(), "initializeBalance")
+
+
+def setup_heat(sf: SoilFluxes3D, cat: Catchment, hour: int = 0, advection: bool = False, latent: bool = True) -> None:
+    """C3 heat configuration: T0 = 288.15 K; HeatSurface boundary on the first soil layer
+    (set by the grid builder) with 2 m measurement heights and 0.01 m roughness; fixed 285.15 K at
+    0.3 m below the free-drainage bottom nodes; total heat flux saved; latent heat on.
+    Advection defaults to OFF: with it on, the reference itself returns NaN temperatures from the
+    first heat sub-step on these catchments (verified with oracle/_ref), so
+    there is nothing to be in parity with."""
+    ns, n = cat.n_surface, cat.n_nodes
+    _ok(sf.initializeHeatFlag(int(HeatFluxSaveMode.Total), advection, latent), "initializeHeatFlag")
+    _ok(sf.set_field(Field.TEMPERATURE, ns, np.full(n - ns, 288.15)), "setNodeTemperature")
+    for f, val in ((Field.BOUNDARY_HEIGHT_WIND, 2.0), (Field.BOUNDARY_HEIGHT_TEMPERATURE, 2.0), (Field.BOUNDARY_ROUGHNESS, 0.01)):
+        _ok(sf.set_field(f, ns, np.full(ns, val)), f.name)
+    _ok(sf.set_fixed_temperature(n - ns, np.full(ns, 285.15), 0.3), "setNodeBoundaryFixedTemperature")
+    set_heat_forcing(sf, cat, hour)
+
+
+def set_heat_forcing(sf: SoilFluxes3D, cat: Catchment, hour: int) -> None:
+    """hourly atmospheric forcing on the HeatSurface nodes: air T 293.15 + 5 sin(2 pi h / 24) K, RH 60 %,
+    wind 2 m/s, net irradiance 400 sin(pi h / 12) W/m2 by day (0 at night)"""
+    ns = cat.n_surface
+    air_t = 293.15 + 5.0 * math.sin(2 * math.pi * hour / 24.0)
+    irr = max(0.0, 400.0 * math.sin(math.pi * (hour % 24) / 12.0))
+    for f, val in ((Field.BOUNDARY_TEMPERATURE, air_t), (Field.BOUNDARY_RELATIVE_HUMIDITY, 60.0),
+                   (Field.BOUNDARY_WIND_SPEED, 2.0), (Field.BOUNDARY_NET_IRRADIANCE, irr)):
+        _ok(sf.set_field(f, ns, np.full(ns, val)), f.name)
 
 
 def run_hours(sf: SoilFluxes3D, cat: Catchment, hours_mm: list[float], max_steps: int | None = None):

@@ -179,6 +179,9 @@ enum sf3d_field {
     SF3D_F_BOUNDARY_TEMPERATURE = 17,    /* setNodeBoundaryTemperature       */
     SF3D_F_BOUNDARY_RELATIVE_HUMIDITY = 18,
     SF3D_F_BOUNDARY_WIND_SPEED  = 19,
+    SF3D_F_BOUNDARY_HEIGHT_WIND = 20,        /* setNodeBoundaryHeightWind        */
+    SF3D_F_BOUNDARY_HEIGHT_TEMPERATURE = 21, /* setNodeBoundaryHeightTemperature */
+    SF3D_F_BOUNDARY_ROUGHNESS   = 22,        /* setNodeBoundaryRoughness         */
     SF3D_F_COUNT
 };
 
@@ -221,8 +224,13 @@ typedef struct sf3d_grid_desc {
     const uint16_t *layer_horizon;    /* layers, horizon index used by setNodeSoil        */
     const uint8_t  *boundary_l1;      /* rows*cols or NULL: 5 Urban / 6 Road on layer 1   */
     int free_catchment_runoff, free_lateral_drainage, free_bottom_drainage;
+    int heat_surface_layer1;          /* 1: layer-1 nodes get the HeatSurface boundary (setNodeBoundary
+                                         after setNode; replaces drainage / urban / road on that layer) */
 } sf3d_grid_desc;
 uint8_t sf3d_ext_build_grid(const sf3d_grid_desc *desc);
+
+/* setNodeBoundaryFixedTemperature(i, T[k], depth) for nodes [first, first+count) */
+uint8_t sf3d_ext_set_fixed_temperature(uint32_t first, uint32_t count, const double *temperature, double depth);
 
 /* counters since sf3d_initialize (what the reference keeps implicit) */
 typedef struct sf3d_counters {

@@ -89,6 +89,14 @@ double __wrap__ZN12soilFluxes3D2v24Heat18GaussSeidelHeatCPUERNS0_9VectorCPUERKNS
     ++g_cnt.heat_sweeps;
     return __real__ZN12soilFluxes3D2v24Heat18GaussSeidelHeatCPUERNS0_9VectorCPUERKNS0_9MatrixCPUERKS2_(x, A, b);
 }
+/* accepted heat sub-steps: Heat::updateHeatBalanceData (heat.cpp:393) is called once per accepted
+   heatLoop (cpusolver.cpp:593) */
+void __real__ZN12soilFluxes3D2v24Heat21updateHeatBalanceDataEv(void);
+void __wrap__ZN12soilFluxes3D2v24Heat21updateHeatBalanceDataEv(void)
+{
+    ++g_cnt.heat_steps;
+    __real__ZN12soilFluxes3D2v24Heat21updateHeatBalanceDataEv();
+}
 } // extern "C"
 
 #define E8(call) static_cast<uint8_t>(call)

@@ -16,13 +16,13 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
 from criteria3d_b200 import REFERENCE_LIB, SoilFluxes3D  # noqa: E402
-from scenarios import SCENARIOS  # noqa: E402
+from scenarios import HEAT_SCENARIOS, SCENARIOS  # noqa: E402
 
 
 def main():
     ref = SoilFluxes3D(REFERENCE_LIB)
     assert ref.backend == "reference"
-    for name, fn in sorted(SCENARIOS.items()):
+    for name, fn in sorted({**SCENARIOS, **HEAT_SCENARIOS}.items()):
         out = fn(ref)
         path = Path(__file__).parent / f"{name}.npz"
         np.savez_compressed(path, **out)

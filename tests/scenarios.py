@@ -8,7 +8,7 @@ from __future__ import annotations
 import numpy as np
 
 from criteria3d_b200 import BoundaryType, Field, LinkType, MeanType, WRCModel
-from criteria3d_b200.synth import Catchment, run_hours, setup, _ok
+from criteria3d_b200.synth import Catchment, run_hours, set_heat_forcing, setup, setup_heat, _ok
 
 FIELDS = (Field.TOTAL_POTENTIAL, Field.WATER_CONTENT, Field.DEGREE_OF_SATURATION, Field.WATER_CONDUCTIVITY,
           Field.BOUNDARY_WATER_FLOW, Field.MAX_FLOW_UP, Field.MAX_FLOW_DOWN, Field.SUM_LATERAL_FLOW)
@@ -27,6 +27,41 @@ def snapshot(sf, n_nodes, dts, n_surface=None):
     out["mbe_mbr"] = np.array([c["last_mbe"], c["last_mbr"], c["delta_t_curr"], c["last_courant"]])
     out["storage"] = np.float64(sf.getWaterStorage())
     return out
+
+
+def heat_snapshot(sf, cat, out):
+    """temperatures and heat-boundary diagnostics of a coupled run (soil nodes only)"""
+    ns, n = cat.n_surface, cat.n_nodes
+    out["TEMPERATURE"] = sf.get_field(Field.TEMPERATURE, ns, n - ns)
+    probe = range(ns, 2 * ns, max(1, ns // 7))
+    out["heat_boundary"] = np.array([[sf.getNodeBoundarySensibleFlux(i), sf.getNodeBoundaryLatentFlux(i),
+                                      sf.getNodeBoundaryRadiativeFlux(i), sf.getNodeBoundaryAerodynamicConductance(i),
+                                      sf.getNodeBoundarySoilConductance(i), sf.getNodeHeatConductivity(i),
+                                      sf.getNodeHeatStorage(i, -1.0), sf.getNodeVapor(i)] for i in probe])
+    out["heat_flux_down"] = np.array([sf.getNodeHeatMaxFlux(i, 2, 0) for i in range(2 * ns, 3 * ns)])
+    c = sf.counters()
+    out["heat_counters"] = np.array([c["heat_steps"], c["heat_sweeps"]], dtype=np.float64)
+    out["heat_mbr_mbe"] = np.array([sf.getHeatMBR(), sf.getHeatMBE()])
+    return out
+
+
+def heat_coupled(sf, threads=1, latent=True):
+    """C3-like: coupled heat (diffusive + latent; see synth.setup_heat for why advection is off),
+    a dry hour with sun then an hour of rain, atmospheric forcing changing per hour"""
+    cat = Catchment(10, 8, 4, heat=True)
+    setup(sf, cat, threads=threads)
+    if not latent:
+        _ok(sf.initializeHeatFlag(1, False, False), "initializeHeatFlag")
+        _ok(sf.initializeBalance(), "balance")
+    dts = []
+    for h, mm in ((10, 0.0), (11, 10.0)):
+        set_heat_forcing(sf, cat, h)
+        dts += run_hours(sf, cat, [mm], max_steps=12)
+    return heat_snapshot(sf, cat, snapshot(sf, cat.n_nodes, dts))
+
+
+def heat_diffusive_only(sf, threads=1):
+    return heat_coupled(sf, threads=threads, latent=False)
 
 
 def storm(sf, shape=(24, 20, 5), hours=(20.0, 40.0), threads=1, max_steps=60, **cat_kw):
@@ -218,12 +253,18 @@ SCENARIOS = {
     "ragged_raster": ragged_raster,
     "scalar_api_column": scalar_api_column,
 }
+HEAT_SCENARIOS = {
+    "heat_coupled": heat_coupled,
+    "heat_diffusive_only": heat_diffusive_only,
+}
 
 
 def compare(a: dict, b: dict, *, exact: bool, h_rel=1e-6, theta_abs=1e-7, flow_rel=1e-6, skip_stale_links=True):
     """exact: bit-identical (oracle restatement vs reference, same libm).  Otherwise the fp64
     tolerances stated in tests/test_gpu_parity.py."""
     assert set(a) == set(b)
+    if exact and "TEMPERATURE" in a:
+        raise AssertionError("heat scenarios are not compared bit-exactly")
     if exact:
         for k in a:
             assert np.array_equal(np.asarray(a[k]), np.asarray(b[k]), equal_nan=True), k
@@ -251,6 +292,16 @@ def compare(a: dict, b: dict, *, exact: bool, h_rel=1e-6, theta_abs=1e-7, flow_r
     assert a["total_water"] == np.float64(b["total_water"]) or abs(a["total_water"] - b["total_water"]) <= 1e-9 * abs(b["total_water"])
     bt, btb = a["boundary_totals"], b["boundary_totals"]
     assert np.all(np.abs(bt - btb) <= flow_rel * np.abs(btb) + 1e-12)
+    if "TEMPERATURE" in a:
+        # heat: the product iterates Jacobi where the reference sweeps Gauss-Seidel (same fixed point,
+        # stopping tolerance 1e-10 K on the update); temperatures rel 1e-6, boundary diagnostics rel 1e-5
+        T, Tb = a["TEMPERATURE"], b["TEMPERATURE"]
+        assert np.max(np.abs(T - Tb) / np.maximum(1.0, np.abs(Tb))) <= 1e-6
+        assert a["heat_counters"][0] == b["heat_counters"][0], "accepted heat sub-steps"
+        hb, hbb = a["heat_boundary"], b["heat_boundary"]
+        assert np.all(np.abs(hb - hbb) <= 1e-5 * np.abs(hbb) + 1e-9)
+        f, fb = a["heat_flux_down"], b["heat_flux_down"]
+        assert np.all(np.abs(f - fb) <= 1e-4 * np.abs(fb) + 1e-3)          # float-rounded accumulations (heat.cpp:203-206)
     if "getters" in a:
         g, gb = a["getters"], b["getters"]
         assert np.all(np.abs(g - gb) <= 1e-6 * np.abs(gb) + 1e-12)

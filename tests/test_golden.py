@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from criteria3d_b200 import ORACLE_LIB, SoilFluxes3D
-from scenarios import SCENARIOS, compare
+from scenarios import HEAT_SCENARIOS, SCENARIOS, compare
 
 GOLDEN = Path(__file__).parent / "golden"
 
@@ -26,6 +26,7 @@ def test_oracle_matches_reference_golden(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", sorted(SCENARIOS))
+@pytest.mark.parametrize("name", sorted({**SCENARIOS, **HEAT_SCENARIOS}))
 def test_product_matches_reference_golden(product, name):
-    compare(SCENARIOS[name](product), _load(name), exact=False)
+    fn = {**SCENARIOS, **HEAT_SCENARIOS}[name]
+    compare(fn(product), _load(name), exact=False)

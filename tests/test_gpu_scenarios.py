@@ -3,7 +3,7 @@
 tests/test_gpu_parity.py."""
 import pytest
 
-from scenarios import SCENARIOS, compare
+from scenarios import HEAT_SCENARIOS, SCENARIOS, compare
 
 pytestmark = pytest.mark.gpu
 
@@ -12,4 +12,14 @@ pytestmark = pytest.mark.gpu
 def test_scenario(product, checker, name):
     a = SCENARIOS[name](product)
     b = SCENARIOS[name](checker)
+    compare(a, b, exact=False)
+
+
+@pytest.mark.parametrize("name", sorted(HEAT_SCENARIOS))
+def test_heat_scenario(product, checker, name):
+    """coupled heat: needs the reference itself as checker (the C restatement covers water only)"""
+    if checker.backend != "reference":
+        pytest.skip("heat parity is checked against oracle/_ref (or its golden vectors, tests/test_golden.py)")
+    a = HEAT_SCENARIOS[name](product)
+    b = HEAT_SCENARIOS[name](checker)
     compare(a, b, exact=False)
