@@ -76,6 +76,7 @@ struct State {
            *b = nullptr, *cap = nullptr, *x0 = nullptr, *x1 = nullptr, *partA = nullptr, *partB = nullptr,
            *partC = nullptr, *scratch = nullptr;
     uint32_t *mcol = nullptr;
+    uint16_t *pid = nullptr; int32_t *pattern = nullptr; bool patternsOk = false;
     Ctrl *ctrl = nullptr;
 
     Engine eng;
@@ -117,7 +118,7 @@ void fill_view()
     v.lidx = S.lidx.d; v.larea = S.larea.d; v.lflow = S.lflow.d; v.lgeom = S.lgeom;
     v.H = S.H.d; v.oldH = S.oldH.d; v.bestH = S.bestH; v.Se = S.Se.d; v.SeOld = S.SeOld; v.K = S.K.d;
     v.wFlow = S.wFlow; v.sink = S.sink.d; v.pond = S.pond.d; v.inv = nullptr;
-    v.mcol = S.mcol; v.mval = S.mval; v.b = S.b; v.cap = S.cap; v.x0 = S.x0; v.x1 = S.x1;
+    v.mcol = S.mcol; v.pid = S.patternsOk ? S.pid : nullptr; v.pattern = S.patternsOk ? S.pattern : nullptr; v.mval = S.mval; v.b = S.b; v.cap = S.cap; v.x0 = S.x0; v.x1 = S.x1;
     v.soil = S.dSoil; v.rough = S.dRough;
     v.culverts = S.culverts.empty() ? nullptr : S.dCulv;
     v.culvertOf = S.culverts.empty() ? nullptr : S.culvertOf.d;
@@ -186,7 +187,11 @@ uint8_t sync_to_device(bool finalizeTopology = true)
     if (S.topoDirty && finalizeTopology)
     {
         int ok = 1;
+        S.patternsOk = false;
+        fill_view();
         k_link_geometry(S.eng.v, &ok);
+        S.patternsOk = k_build_patterns(S.eng.v, S.pid, S.pattern) && getenv("SF3D_EXPLICIT_INDEX") == nullptr;
+        fill_view();
         S.topoDirty = false;
         if (!ok)
         {
@@ -261,6 +266,7 @@ void release_all()
                           &S.partA, &S.partB, &S.partC, &S.scratch};
     for (double **p : devOnly) { dev_free(*p); *p = nullptr; }
     dev_free(S.mcol); S.mcol = nullptr;
+    dev_free(S.pid); S.pid = nullptr; dev_free(S.pattern); S.pattern = nullptr; S.patternsOk = false;
     dev_free(S.ctrl); S.ctrl = nullptr;
 }
 
@@ -297,6 +303,7 @@ uint8_t sf3d_initialize(uint32_t nrNodes, uint32_t nrSurfaceNodes, uint8_t nrLat
         S.culvertOf.alloc(nrSurfaceNodes);
         S.bestH = (double *)dev_alloc(N * 8); S.SeOld = (double *)dev_alloc(N * 8); S.wFlow = (double *)dev_alloc(N * 8);
         S.lgeom = (double *)dev_alloc(L * 8); S.mval = (double *)dev_alloc(L * 8); S.mcol = (uint32_t *)dev_alloc(L * 4);
+        S.pid = (uint16_t *)dev_alloc(N * 2); S.pattern = (int32_t *)dev_alloc(pattern_table_bytes());
         S.b = (double *)dev_alloc(N * 8); S.cap = (double *)dev_alloc(N * 8);
         S.x0 = (double *)dev_alloc(N * 8); S.x1 = (double *)dev_alloc(N * 8);
         const size_t nb = (size_t)reduce_blocks(0xFFFFFFFFu);

@@ -230,6 +230,72 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_link_geometry(SF3DView v, int
     }
 }
 
+// ---- pattern compression of the column indices ------------------------------------------------
+// For every node the ten column offsets (mcol[c][i] - i) form a "link pattern"; a DEM catchment has a
+// few dozen distinct ones (interior, edges, corners x top/middle/bottom layer; more for ragged
+// rasters).  Patterns are deduplicated in a small device hash table; each node keeps a 16-bit pattern
+// id, so the sweep reads 2 bytes of index data per node instead of 40.  kern_verify_patterns then
+// proves  i + pattern[pid[i]][c] == mcol[c][i]  for every entry (bit-exact integer map) or the
+// explicit index array stays in use.
+#define SF3D_PATTERN_SLOTS 1024
+__device__ __forceinline__ unsigned long long pattern_hash(const int32_t *off)
+{
+    unsigned long long h = 0x9E3779B97F4A7C15ull;
+    #pragma unroll
+    for (int c = 0; c < SF3D_NLINK; ++c)
+    {
+        h ^= (unsigned long long)(uint32_t)off[c] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+        h *= 0xBF58476D1CE4E5B9ull;
+    }
+    return h ? h : 1ull;            // 0 marks an empty slot
+}
+__global__ void __launch_bounds__(SF3D_BLOCK) kern_build_patterns(SF3DView v, unsigned long long *keys, int32_t *table,
+                                                                  uint16_t *pid, int *overflow)
+{
+    const size_t N = v.N;
+    for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
+    {
+        int32_t off[SF3D_NLINK];
+        bool fits = true;
+        #pragma unroll
+        for (int c = 0; c < SF3D_NLINK; ++c)
+        {
+            const long long d = (long long)v.mcol[(size_t)c * N + i] - (long long)i;
+            if (d > 2147483647ll || d < -2147483647ll) fits = false;
+            off[c] = (int32_t)d;
+        }
+        if (!fits) { *overflow = 1; pid[i] = 0; continue; }
+        const unsigned long long h = pattern_hash(off);
+        uint32_t slot = (uint32_t)(h % SF3D_PATTERN_SLOTS);
+        bool placed = false;
+        for (int probe = 0; probe < SF3D_PATTERN_SLOTS; ++probe)
+        {
+            const unsigned long long old = atomicCAS(&keys[slot], 0ull, h);
+            if (old == 0ull)
+            {
+                #pragma unroll
+                for (int c = 0; c < SF3D_NLINK; ++c) table[slot * SF3D_NLINK + c] = off[c];
+                placed = true; break;
+            }
+            if (old == h) { placed = true; break; }
+            slot = (slot + 1) % SF3D_PATTERN_SLOTS;
+        }
+        if (!placed) *overflow = 1;
+        pid[i] = (uint16_t)slot;
+    }
+}
+__global__ void __launch_bounds__(SF3D_BLOCK) kern_verify_patterns(SF3DView v, const int32_t *table, const uint16_t *pid, int *mismatch)
+{
+    const size_t N = v.N;
+    for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
+    {
+        const int32_t *off = table + (size_t)pid[i] * SF3D_NLINK;
+        #pragma unroll
+        for (int c = 0; c < SF3D_NLINK; ++c)
+            if ((uint32_t)((int64_t)i + off[c]) != v.mcol[(size_t)c * N + i]) *mismatch = 1;
+    }
+}
+
 __global__ void __launch_bounds__(SF3D_BLOCK) kern_begin_try(SF3DView v)
 {
     for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
@@ -242,10 +308,11 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_restore_old(SF3DView v)
         sf3d_row_restore_old(v, i);
 }
 
+template <bool HEAT>
 __global__ void __launch_bounds__(SF3D_BLOCK) kern_node_phase(SF3DView v, double dt, int withCapacity)
 {
     for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
-        sf3d_row_node_phase(v, i, dt, withCapacity);
+        sf3d_row_node_phase<HEAT>(v, i, dt, withCapacity);
 }
 
 // the stopping / Courant rules, applied either by the last block of the producing kernel (single
@@ -284,6 +351,7 @@ __global__ void kern_rule_boundary(Ctrl *c) { c->boundarySum = c->red[0]; }
 // link phase: conductances, diagonal, row normalisation, right-hand side, per-row Courant;
 // the last block publishes max Courant and arms the on-device solver state
 // (CPUSolver::checkCourant test, cpusolver.cpp:248-260).  Ghost rows are not assembled.
+template <bool HEAT>
 __global__ void __launch_bounds__(SF3D_BLOCK) kern_assemble(SF3DView v, double dt, int approx, double dtMin)
 {
     __shared__ double sh[SF3D_BLOCK / 32];
@@ -291,7 +359,7 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_assemble(SF3DView v, double d
     for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
     {
         if (v.world > 1 && META_GHOST(v.meta[i])) continue;
-        const double c = sf3d_row_assemble(v, i, dt, approx);
+        const double c = sf3d_row_assemble<HEAT>(v, i, dt, approx);
         courant = (courant < c) ? c : courant;
     }
     courant = block_reduce<true>(courant, sh);
@@ -874,12 +942,38 @@ void k_link_geometry(const SF3DView &v, int *surfaceOrderOk)
     d2h(surfaceOrderOk, flag, sizeof(int));
     dev_free(flag);
 }
+// returns true when the pattern-compressed index map reproduces mcol exactly
+bool k_build_patterns(const SF3DView &v, uint16_t *pid, int32_t *table)
+{
+    unsigned long long *keys = (unsigned long long *)dev_alloc(SF3D_PATTERN_SLOTS * sizeof(unsigned long long));
+    int *flags = (int *)dev_alloc(2 * sizeof(int));
+    dev_zero(table, (size_t)SF3D_PATTERN_SLOTS * SF3D_NLINK * sizeof(int32_t));
+    kern_build_patterns<<<GRID(v.N)>>>(v, keys, table, pid, flags); LAUNCH_CHECK();
+    kern_verify_patterns<<<GRID(v.N)>>>(v, table, pid, flags + 1); LAUNCH_CHECK();
+    int h[2] = {1, 1};
+    d2h(h, flags, sizeof h);
+    dev_free(keys); dev_free(flags);
+    return h[0] == 0 && h[1] == 0;
+}
+size_t pattern_table_bytes() { return (size_t)SF3D_PATTERN_SLOTS * SF3D_NLINK * sizeof(int32_t); }
+
 void k_begin_try(const SF3DView &v) { ProfScope ps(SF3D_K_BEGIN_TRY); kern_begin_try<<<GRID(v.N)>>>(v); LAUNCH_CHECK(); }
 void k_restore_old(const SF3DView &v) { ProfScope ps(SF3D_K_OTHER); kern_restore_old<<<GRID(v.N)>>>(v); LAUNCH_CHECK(); }
-void k_node_phase(const SF3DView &v, double dt, int withCapacity) { ProfScope ps(SF3D_K_NODE_PHASE); kern_node_phase<<<GRID(v.N)>>>(v, dt, withCapacity); LAUNCH_CHECK(); }
+void k_node_phase(const SF3DView &v, double dt, int withCapacity)
+{
+    ProfScope ps(SF3D_K_NODE_PHASE);
+    if (v.computeHeat) kern_node_phase<true><<<GRID(v.N)>>>(v, dt, withCapacity);
+    else kern_node_phase<false><<<GRID(v.N)>>>(v, dt, withCapacity);
+    LAUNCH_CHECK();
+}
 void k_assemble(const SF3DView &v, double dt, int approx, double dtMin)
 {
-    { ProfScope ps(SF3D_K_ASSEMBLE); kern_assemble<<<GRID(v.N)>>>(v, dt, approx, dtMin); LAUNCH_CHECK(); }
+    {
+        ProfScope ps(SF3D_K_ASSEMBLE);
+        if (v.computeHeat) kern_assemble<true><<<GRID(v.N)>>>(v, dt, approx, dtMin);
+        else kern_assemble<false><<<GRID(v.N)>>>(v, dt, approx, dtMin);
+        LAUNCH_CHECK();
+    }
     if (v.world > 1)
     {
         comm_allreduce(v.ctrl->red, 1, true);

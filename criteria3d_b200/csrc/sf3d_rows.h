@@ -167,6 +167,8 @@ SF3D_HD double sf3d_culvert_flow(double waterLevel, double pond, double width, d
     return flow;
 }
 
+// HEAT is a compile-time switch so that the water-only kernels carry none of the heat closures
+template <bool HEAT>
 SF3D_HD void sf3d_row_node_phase(const SF3DView &v, uint32_t i, double dt, int withCapacity)
 {
     const uint32_t m = v.meta[i];
@@ -180,13 +182,13 @@ SF3D_HD void sf3d_row_node_phase(const SF3DView &v, uint32_t i, double dt, int w
         const double Se = v.Se[i];
         // computeNodeK (soilPhysics.cpp:164-172)
         K = sf3d_mualem(s, v.wrcModel, Se);
-        if (v.computeHeat && v.computeHeatVapor) K += sf3d_heat_vapor_K(v, i);
+        if (HEAT && v.computeHeatVapor) K += sf3d_heat_vapor_K(v, i);
         v.K[i] = K;
         if (withCapacity)
         {
             const double dThetadH = sf3d_dtheta_dh(s, v.wrcModel, H, oldH, z, Se, v.SeOld[i]);
             double c = v.size[i] * dThetadH;
-            if (v.computeHeat && v.computeHeatVapor) c += v.size[i] * sf3d_heat_dthetav_dh(v, i, dThetadH);
+            if (HEAT && v.computeHeatVapor) c += v.size[i] * sf3d_heat_dthetav_dh(v, i, dThetadH);
             v.cap[i] = c;
         }
     }
@@ -205,7 +207,7 @@ SF3D_HD void sf3d_row_node_phase(const SF3DView &v, uint32_t i, double dt, int w
     // under OpenMP); the sequential order is reproduced: applied after the node's own terms.
     int evapActive = 0;
     double surfEvap = 0.;
-    if (surface && v.computeHeat && v.computeHeatVapor) surfEvap = sf3d_heat_surface_pull(v, i, dt, &evapActive);
+    if (HEAT && surface && v.computeHeatVapor) surfEvap = sf3d_heat_surface_pull(v, i, dt, &evapActive);
 
     const uint32_t bt = META_BT(m);
     if (bt == BT_NONE)
@@ -249,7 +251,7 @@ SF3D_HD void sf3d_row_node_phase(const SF3DView &v, uint32_t i, double dt, int w
             break;
         }
         case BT_HEAT_SURFACE:
-            if (v.computeHeat && v.computeHeatVapor) rate = sf3d_heat_surface_boundary(v, i, dt, nullptr);
+            if (HEAT && v.computeHeatVapor) rate = sf3d_heat_surface_boundary(v, i, dt, nullptr);
             break;
         case BT_CULVERT:
         {
@@ -383,16 +385,29 @@ SF3D_HD void sf3d_row_store(const SF3DView &v, uint32_t i, double dt, const doub
     v.b[i] = rhs * invDiag;                           // cpusolver.cpp:300
 }
 
+// linked node of matrix column c of row i: through the per-node link pattern when available
+// (2 bytes per node instead of 40), else through the explicit column-index array
+SF3D_HD uint32_t sf3d_col_index(const SF3DView &v, const int32_t *__restrict__ off, uint32_t i, int c)
+{
+    return off ? (uint32_t)((int64_t)i + off[c]) : v.mcol[(size_t)c * v.N + i];
+}
+SF3D_HD const int32_t *sf3d_row_pattern(const SF3DView &v, uint32_t i)
+{
+    return v.pid ? v.pattern + (size_t)v.pid[i] * SF3D_NLINK : nullptr;
+}
+
 // soil row: every link is a redistribution except an Up link to a surface node (infiltration).
 // The ten neighbour conductivities are gathered first (independent loads), then the means.
+template <bool HEAT>
 SF3D_HD double sf3d_row_assemble_soil(const SF3DView &v, uint32_t i, double dt)
 {
     const size_t N = v.N;
     const double ki = v.K[i];
     uint32_t j[SF3D_NLINK];
     double g[SF3D_NLINK], kj[SF3D_NLINK], k[SF3D_NLINK];
+    const int32_t *off = sf3d_row_pattern(v, i);
     #pragma unroll
-    for (int c = 0; c < SF3D_NLINK; ++c) { j[c] = v.mcol[(size_t)c * N + i]; g[c] = v.lgeom[(size_t)c * N + i]; }
+    for (int c = 0; c < SF3D_NLINK; ++c) { j[c] = sf3d_col_index(v, off, i, c); g[c] = SF3D_LDS(v.lgeom + (size_t)c * N + i); }
     #pragma unroll
     for (int c = 0; c < SF3D_NLINK; ++c) kj[c] = v.K[j[c]];
 
@@ -412,7 +427,7 @@ SF3D_HD double sf3d_row_assemble_soil(const SF3DView &v, uint32_t i, double dt)
             const double area = 0.;
 #endif
             kc = sf3d_redistribution(v, ki, kj[c], slot, area, g[c]);
-            if (v.computeHeat && j[c] != i) invariant += sf3d_heat_thermal_invariant(v, i, slot, j[c]);
+            if (HEAT && j[c] != i) invariant += sf3d_heat_thermal_invariant(v, i, slot, j[c]);
         }
         k[c] = kc;
         sum += kc;                                    // zero entries are not stored in the reference; +0 is exact
@@ -448,9 +463,10 @@ SF3D_HD double sf3d_row_assemble_surface(const SF3DView &v, uint32_t i, double d
     return courant;
 }
 
+template <bool HEAT>
 SF3D_HD double sf3d_row_assemble(const SF3DView &v, uint32_t i, double dt, int approx)
 {
-    return (i < v.Ns) ? sf3d_row_assemble_surface(v, i, dt, approx) : sf3d_row_assemble_soil(v, i, dt);
+    return (i < v.Ns) ? sf3d_row_assemble_surface(v, i, dt, approx) : sf3d_row_assemble_soil<HEAT>(v, i, dt);
 }
 
 // ==========================================================================================
@@ -459,15 +475,16 @@ SF3D_HD double sf3d_row_assemble(const SF3DView &v, uint32_t i, double dt, int a
 SF3D_HD double sf3d_row_jacobi(const SF3DView &v, uint32_t i, const double *__restrict__ xin, double *__restrict__ xout)
 {
     const size_t N = v.N;
-    double xnew = v.b[i];
+    const int32_t *off = sf3d_row_pattern(v, i);
+    double xnew = SF3D_LDS(v.b + i);
     #pragma unroll
     for (int c = 0; c < SF3D_NLINK; ++c)
     {
-        const double A = v.mval[(size_t)c * N + i];
-        const uint32_t j = v.mcol[(size_t)c * N + i];
+        const double A = SF3D_LDS(v.mval + (size_t)c * N + i);
+        const uint32_t j = sf3d_col_index(v, off, i, c);
         xnew -= A * xin[j];
     }
-    const double z = v.z[i];
+    const double z = SF3D_LDS(v.z + i);
     if (i < v.Ns) xnew = sf3d_max(xnew, z);
     const double xold = xin[i];
     double norm = fabs(xnew - xold);

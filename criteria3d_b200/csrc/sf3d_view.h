@@ -16,6 +16,14 @@
 #define SF3D_HD inline
 #endif
 
+// streaming loads: matrix values, right-hand side and static geometry are read once per pass; mark
+// them evict-first so that the 126 MB L2 keeps the gathered vectors (x, K, H) instead
+#if defined(__CUDA_ARCH__)
+#define SF3D_LDS(p) __ldcs(p)
+#else
+#define SF3D_LDS(p) (*(p))
+#endif
+
 #define SF3D_NLINK 10           // maxTotalLink, types.h:25
 #define SF3D_NODATA (-9999.0)   // commonConstants.h:31
 
@@ -101,6 +109,10 @@ struct SF3DView {
     double *H, *oldH, *bestH, *Se, *SeOld, *K, *wFlow, *sink, *pond, *inv;
     // linear system, COLUMN-major: [col*N + i]; mcol is static
     uint32_t *mcol;
+    // pattern-compressed column indices: mcol[c][i] == i + pattern[pid[i]*10 + c] for every node
+    // (verified bit-exactly at finalize); null when the graph has too many distinct link patterns
+    const uint16_t *pid;
+    const int32_t *pattern;
     double *mval;
     double *b, *cap, *x0, *x1;
     // tables

@@ -77,3 +77,21 @@ def test_trajectory(product, checker, shape, hours):
     assert cg["steps"] == co["steps"] and cg["approximations"] == co["approximations"]
     sink_total = sum(np.sum(np.abs(cat.rain_sink_source(mm))) * 3600.0 for mm in hours)
     assert abs(cg["last_mbe"] - co["last_mbe"]) <= 1e-6 * sink_total
+
+
+def test_pattern_compressed_indices_are_bit_identical(product, checker, monkeypatch):
+    """The sweep reads the column indices through 16-bit link patterns (2 B/node instead of 40 B).
+    The map is verified on the device at finalize; forcing the explicit index array must give
+    bit-identical potentials (integer work: exact)."""
+    cat = Catchment(33, 27, 5)
+    runs = []
+    for explicit in (False, True):
+        if explicit:
+            monkeypatch.setenv("SF3D_EXPLICIT_INDEX", "1")
+        else:
+            monkeypatch.delenv("SF3D_EXPLICIT_INDEX", raising=False)
+        setup(product, cat)
+        dts = run_hours(product, cat, [30.0], max_steps=25)
+        runs.append((dts, product.get_field(Field.TOTAL_POTENTIAL, 0, cat.n_nodes), product.counters()["sweeps"]))
+    assert runs[0][0] == runs[1][0] and runs[0][2] == runs[1][2]
+    assert np.array_equal(runs[0][1], runs[1][1])
