@@ -56,6 +56,30 @@ def _hash01(seed: int, a: np.ndarray, b: np.ndarray) -> np.ndarray:
     return (x >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
 
 
+def _raster_slope_and_outlet(dem: np.ndarray, valid: np.ndarray, cell: float):
+    """Harness-side stand-in for gis::computeSlopeAspectMaps / gis::isBoundaryRunoff (agrolib/gis, out of
+    scope): slope = gradient magnitude over valid neighbours; outlet = valid cells on the
+    catchment rim (next to NODATA or the raster edge) lying below the mean of their valid neighbours."""
+    R, C = dem.shape
+    z = np.where(valid, dem.astype(np.float64), np.nan)
+    zp = np.pad(z, 1, constant_values=np.nan)
+    nb = np.stack([zp[1 + di: 1 + di + R, 1 + dj: 1 + dj + C] for di in (-1, 0, 1) for dj in (-1, 0, 1) if (di, dj) != (0, 0)])
+    def diff(a, b):
+        d = (a - b) / (2 * cell)
+        one = np.where(np.isnan(a), (z - b) / cell, (a - z) / cell)
+        return np.where(np.isnan(a) | np.isnan(b), np.where(np.isnan(one), 0.0, one), d)
+    gx = diff(zp[1:-1, 2:], zp[1:-1, :-2])
+    gy = diff(zp[2:, 1:-1], zp[:-2, 1:-1])
+    slope = np.where(valid, np.sqrt(gx * gx + gy * gy), 0.0)
+    rim = valid & np.isnan(nb).any(axis=0)
+    import warnings
+    with np.errstate(invalid="ignore"), warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        lower = z < np.nanmean(nb, axis=0)
+    outlet = (rim & lower).astype(np.uint8)
+    return np.ascontiguousarray(slope, dtype=np.float32), np.ascontiguousarray(outlet)
+
+
 def soil_layers(n_soil_layers: int, min_t=0.02, max_t=0.10, max_t_depth=0.40):
     """Layer thickness/centre-depth progression of Project3D::setSoilLayers/setLayersDepth
     (project3D.cpp:1568-1661), truncated/extended to exactly `n_soil_layers` soil layers.
@@ -98,6 +122,9 @@ class Catchment:
     initial_psi: float = -2.0
     row0: int = 0                        # first global DEM row of this (slab of the) raster
     global_rows: int | None = None       # rows of the whole catchment (None: this raster is the whole)
+    valid: np.ndarray | None = field(default=None, repr=False)      # bool rows x cols, False = NODATA cell
+    dem_override: np.ndarray | None = field(default=None, repr=False)   # use this DEM instead of the generator
+    soil_override: np.ndarray | None = field(default=None, repr=False)  # soil id per cell
     # filled by __post_init__
     dem: np.ndarray = field(init=False, repr=False)
     slope_tan: np.ndarray = field(init=False, repr=False)
@@ -121,15 +148,31 @@ class Catchment:
         z = (200.0 + cell * (0.03 * (RG - 1 - r) + 0.01 * c)
              + 5.0 * np.sin(2 * np.pi * r / 257.0) * np.cos(2 * np.pi * c / 193.0) + 0.25 * u)
         self.dem = np.ascontiguousarray(z, dtype=np.float32)
+        if self.dem_override is not None:
+            self.dem = np.ascontiguousarray(self.dem_override, dtype=np.float32)
+            assert self.dem.shape == (R, Cc)
         # analytic slope of the smooth part of the DEM (independent of how the raster is cut into slabs)
         gy = -0.03 + 5.0 * (2 * np.pi / 257.0 / cell) * np.cos(2 * np.pi * r / 257.0) * np.cos(2 * np.pi * c / 193.0)
         gx = 0.01 - 5.0 * (2 * np.pi / 193.0 / cell) * np.sin(2 * np.pi * r / 257.0) * np.sin(2 * np.pi * c / 193.0)
         self.slope_tan = np.ascontiguousarray(np.sqrt(gx * gx + gy * gy), dtype=np.float32)
-        self.cell_rank = np.arange(R * Cc, dtype=np.int32).reshape(R, Cc)
         self.outlet = np.zeros((R, Cc), np.uint8)
-        if self.row0 + R == RG:
-            self.outlet[R - 1, :] = 1                   # outlet edge = last row of the whole catchment
+        if self.valid is None:
+            self.cell_rank = np.arange(R * Cc, dtype=np.int32).reshape(R, Cc)
+            if self.row0 + R == RG:
+                self.outlet[R - 1, :] = 1               # outlet edge = last row of the whole catchment
+        else:
+            valid = np.ascontiguousarray(self.valid, dtype=bool)
+            assert valid.shape == (R, Cc)
+            rank = np.full((R, Cc), -1, np.int32)
+            rank[valid] = np.arange(int(valid.sum()), dtype=np.int32)
+            self.cell_rank = np.ascontiguousarray(rank)
+            if self.dem_override is not None:
+                self.slope_tan, self.outlet = _raster_slope_and_outlet(self.dem, valid, cell)
+            elif self.row0 + R == RG:
+                self.outlet[R - 1, :] = valid[R - 1, :]
         self.soil_id = (np.floor(_hash01(self.seed + 1, ri // 64, ci // 64) * 4).astype(np.uint16) % 4)
+        if self.soil_override is not None:
+            self.soil_id = np.ascontiguousarray(self.soil_override, dtype=np.uint16)
         rough = _hash01(self.seed + 2, ri, ci) < 0.10
         self.surface_id = np.ascontiguousarray(rough.astype(np.uint16))
         self.pond = np.where(rough, SURFACE_TABLE[1][1], SURFACE_TABLE[0][1]).astype(np.float64)
@@ -144,7 +187,7 @@ class Catchment:
 
     @property
     def n_surface(self) -> int:
-        return self.rows * self.cols
+        return self.rows * self.cols if self.valid is None else int(np.count_nonzero(self.valid))
 
     @property
     def n_nodes(self) -> int:
@@ -182,7 +225,8 @@ class Catchment:
         c = np.arange(self.cols, dtype=np.float64)[None, :]
         scale = 1.0 + 0.3 * np.sin(2 * np.pi * c / self.cols) + np.zeros((self.rows, 1))
         area = self.cell * self.cell
-        return np.ascontiguousarray((area * mm_per_hour * scale / 1000.0 / 3600.0).reshape(-1))
+        q = area * mm_per_hour * scale / 1000.0 / 3600.0
+        return np.ascontiguousarray(q.reshape(-1) if self.valid is None else q[np.asarray(self.valid, bool)])
 
     def initial_matric_potential(self) -> np.ndarray:
         psi = np.full(self.n_nodes, self.initial_psi, np.float64)

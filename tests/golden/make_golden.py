@@ -19,7 +19,18 @@ from criteria3d_b200 import REFERENCE_LIB, SoilFluxes3D  # noqa: E402
 from scenarios import HEAT_SCENARIOS, SCENARIOS  # noqa: E402
 
 
+def config1_inputs():
+    """rasters of the bundled STH sample project -> tests/golden/config1_sth_inputs.npz"""
+    from criteria3d_b200.raster import read_flt
+    base = Path("/root/reference/DATA/PROJECT/STH")
+    dem = read_flt(base / "MAPS" / "DEM_STH.flt")
+    soil = read_flt(base / "SOIL" / "soilMap_STH.flt")
+    np.savez_compressed(Path(__file__).parent / "config1_sth_inputs.npz", dem=dem.values, soil=soil.values,
+                        cell=np.float64(dem.cell), xll=np.float64(dem.xll), yll=np.float64(dem.yll))
+
+
 def main():
+    config1_inputs()
     ref = SoilFluxes3D(REFERENCE_LIB)
     assert ref.backend == "reference"
     for name, fn in sorted({**SCENARIOS, **HEAT_SCENARIOS}.items()):

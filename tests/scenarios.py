@@ -139,24 +139,31 @@ def saturated_bottom(sf, threads=1):
 
 def ragged_raster(sf, threads=1):
     """NODATA holes and a ragged edge: nodes with fewer than 8 lateral links"""
-    cat = Catchment(22, 18, 4)
-    valid = np.ones((cat.rows, cat.cols), bool)
+    valid = np.ones((22, 18), bool)
     valid[0:3, 0:5] = False
     valid[9:12, 7:10] = False
-    valid[:, -1] = np.arange(cat.rows) % 3 != 0
-    rank = np.full((cat.rows, cat.cols), -1, np.int32)
-    rank[valid] = np.arange(valid.sum(), dtype=np.int32)
-    cat.cell_rank = np.ascontiguousarray(rank)
-    nv = int(valid.sum())
-    type(cat).n_surface.fget  # property stays; override sizes through a subclass-free trick below
-    cat.__class__ = type("RaggedCatchment", (Catchment,), {"n_surface": property(lambda self: nv)})
-    sink_full = cat.rain_sink_source
-
-    def rain(mm):
-        return np.ascontiguousarray(Catchment.rain_sink_source(cat, mm).reshape(cat.rows, cat.cols)[valid])
-    cat.rain_sink_source = rain
+    valid[:, -1] = np.arange(22) % 3 != 0
+    cat = Catchment(22, 18, 4, valid=valid)
     setup(sf, cat, threads=threads)
     dts = run_hours(sf, cat, [30.0], max_steps=40)
+    return snapshot(sf, cat.n_nodes, dts)
+
+
+def config1_bundled_catchment(sf, threads=1, hours=8, max_steps=100):
+    """BASELINE config 1: the bundled STH sample catchment (DATA/PROJECT/STH/MAPS/DEM_STH.flt, 34 x 139
+    cells of 2 m, 1244 NODATA cells; soil map ids 1-3), water only, 2 mm/h rain.  The full 24 h run is
+    17 841 accepted steps (dt is Courant-limited to ~5 s on 2 m cells; 15 min on one CPU thread), so the
+    parity case is bounded to the first 100 accepted steps (about 5 simulated hours); bench-style full runs are left to the harness.
+    The rasters are committed as tests/golden/config1_sth_inputs.npz (made by make_golden.py with
+    criteria3d_b200/raster.py from the reference's DATA directory)."""
+    from pathlib import Path
+    with np.load(Path(__file__).parent / "golden" / "config1_sth_inputs.npz") as z:
+        dem, soil, cell = z["dem"], z["soil"], float(z["cell"])
+    valid = dem != np.float32(-9999)
+    cat = Catchment(dem.shape[0], dem.shape[1], 5, cell=cell, valid=valid, dem_override=np.where(valid, dem, 0).astype(np.float32),
+                    soil_override=np.where(valid, soil, 1).astype(np.uint16))
+    setup(sf, cat, threads=threads)
+    dts = run_hours(sf, cat, [2.0] * hours, max_steps=max_steps)
     return snapshot(sf, cat.n_nodes, dts)
 
 
@@ -251,6 +258,7 @@ SCENARIOS = {
     "prescribed_and_urban": prescribed_and_urban,
     "saturated_bottom": saturated_bottom,
     "ragged_raster": ragged_raster,
+    "config1_bundled_catchment": config1_bundled_catchment,
     "scalar_api_column": scalar_api_column,
 }
 HEAT_SCENARIOS = {
