@@ -271,8 +271,6 @@ def compare(a: dict, b: dict, *, exact: bool, h_rel=1e-6, theta_abs=1e-7, flow_r
     """exact: bit-identical (oracle restatement vs reference, same libm).  Otherwise the fp64
     tolerances stated in tests/test_gpu_parity.py."""
     assert set(a) == set(b)
-    if exact and "TEMPERATURE" in a:
-        raise AssertionError("heat scenarios are not compared bit-exactly")
     if exact:
         for k in a:
             assert np.array_equal(np.asarray(a[k]), np.asarray(b[k]), equal_nan=True), k

@@ -17,12 +17,12 @@ def _load(name):
         return {k: z[k] for k in z.files}
 
 
-@pytest.mark.parametrize("name", sorted(SCENARIOS))
+@pytest.mark.parametrize("name", sorted({**SCENARIOS, **HEAT_SCENARIOS}))
 def test_oracle_matches_reference_golden(name):
     if not ORACLE_LIB.exists():
         pytest.skip("oracle/libsf3d_oracle.so not built")
     port = SoilFluxes3D(ORACLE_LIB)
-    compare(SCENARIOS[name](port), _load(name), exact=True)
+    compare({**SCENARIOS, **HEAT_SCENARIOS}[name](port), _load(name), exact=True)
 
 
 @pytest.mark.gpu

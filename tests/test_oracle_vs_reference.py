@@ -5,7 +5,9 @@ import numpy as np
 import pytest
 
 from criteria3d_b200 import ORACLE_LIB, REFERENCE_LIB, SoilFluxes3D
-from scenarios import SCENARIOS, compare
+from scenarios import HEAT_SCENARIOS, SCENARIOS, compare
+
+ALL = {**SCENARIOS, **HEAT_SCENARIOS}
 
 pytestmark = pytest.mark.skipif(not (ORACLE_LIB.exists() and REFERENCE_LIB.exists()),
                                 reason="needs oracle/libsf3d_oracle.so and oracle/_ref/libsf3d_ref.so")
@@ -16,11 +18,11 @@ def libs():
     return SoilFluxes3D(ORACLE_LIB), SoilFluxes3D(REFERENCE_LIB)
 
 
-@pytest.mark.parametrize("name", sorted(SCENARIOS))
+@pytest.mark.parametrize("name", sorted(ALL))
 def test_bit_identical(libs, name):
     port, ref = libs
-    a = SCENARIOS[name](port)
-    b = SCENARIOS[name](ref)
+    a = ALL[name](port)
+    b = ALL[name](ref)
     compare(a, b, exact=True)
 
 
