@@ -250,6 +250,8 @@ _EXT = [
     ("sf3d_ext_comm_unique_id", u8, [C.POINTER(u8)]),
     ("sf3d_ext_comm_init", u8, [cint, cint, C.POINTER(u8)]),
     ("sf3d_ext_comm_finalize", u8, []),
+    ("sf3d_ext_ipc_export", u8, [C.POINTER(u8)]),
+    ("sf3d_ext_ipc_import", u8, [cint, C.POINTER(u8), u32, C.POINTER(u32)]),
     ("sf3d_ext_set_halo", u8, [u32, C.POINTER(C.c_int32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32),
                                C.POINTER(u32), C.c_uint64]),
     ("sf3d_ext_stream", C.c_void_p, []),
@@ -346,6 +348,18 @@ class SoilFluxes3D:
     def comm_init(self, rank: int, world: int, uid: bytes) -> int:
         buf = (u8 * 128).from_buffer_copy(uid)
         return self.lib.sf3d_ext_comm_init(rank, world, buf)
+
+    def ipc_export(self) -> bytes:
+        buf = (u8 * 128)()
+        rc = self.lib.sf3d_ext_ipc_export(buf)
+        if rc:
+            raise RuntimeError(f"sf3d_ext_ipc_export -> {SF3Derror(rc).name}")
+        return bytes(buf)
+
+    def ipc_import(self, peer: int, handles: bytes, remote_idx) -> int:
+        buf = (u8 * 128).from_buffer_copy(handles)
+        r = np.ascontiguousarray(remote_idx, dtype=np.uint32)
+        return self.lib.sf3d_ext_ipc_import(peer, buf, r.size, _ptr(r, u32))
 
     def comm_finalize(self) -> int:
         return self.lib.sf3d_ext_comm_finalize()

@@ -1128,6 +1128,19 @@ uint8_t sf3d_ext_comm_init(int rank, int world, const uint8_t id[128])
     if (S.initialized) return SF3D_PARAMETER_ERROR;     // wire the ranks before initializeSF3D
     return guarded([&]() -> uint8_t { dev_select(g_device); comm_init(rank, world, id); return SF3D_OK; }, (uint8_t)SF3D_SOLVER_ERROR);
 }
+uint8_t sf3d_ext_ipc_export(uint8_t handles[128])
+{
+    return guarded([&]() -> uint8_t { REQUIRE_INIT_E(); comm_ipc_export(S.x0, S.x1, handles); return SF3D_OK; }, (uint8_t)SF3D_SOLVER_ERROR);
+}
+uint8_t sf3d_ext_ipc_import(int peer, const uint8_t handles[128], uint32_t n, const uint32_t *remoteIdx)
+{
+    return guarded([&]() -> uint8_t {
+        REQUIRE_INIT_E();
+        if (!handles || (n && !remoteIdx)) return SF3D_PARAMETER_ERROR;
+        comm_ipc_import(peer, handles, n, remoteIdx);
+        return SF3D_OK;
+    }, (uint8_t)SF3D_SOLVER_ERROR);
+}
 uint8_t sf3d_ext_comm_finalize(void)
 { return guarded([&]() -> uint8_t { comm_finalize(); return SF3D_OK; }, (uint8_t)SF3D_SOLVER_ERROR); }
 uint8_t sf3d_ext_set_halo(uint32_t nPeers, const int32_t *peers, const uint32_t *sendCount, const uint32_t *sendIdx,

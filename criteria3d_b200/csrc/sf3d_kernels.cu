@@ -409,6 +409,15 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_pack(const double *__restrict
 {
     for (uint32_t k = blockIdx.x * SF3D_BLOCK + threadIdx.x; k < n; k += gridDim.x * SF3D_BLOCK) buf[k] = x[idx[k]];
 }
+// direct halo: store my boundary values into the neighbour's ghost entries (peer memory, NVLink)
+__global__ void __launch_bounds__(SF3D_BLOCK) kern_push(const double *__restrict__ x, const uint32_t *__restrict__ idx, uint32_t n,
+                                                      double *__restrict__ peerX, const uint32_t *__restrict__ remoteIdx,
+                                                      const Ctrl *ctrl)
+{
+    if (ctrl && ctrl->status != SOLVE_RUNNING) return;          // sweeps launched after the solve ended do nothing
+    for (uint32_t k = blockIdx.x * SF3D_BLOCK + threadIdx.x; k < n; k += gridDim.x * SF3D_BLOCK) peerX[remoteIdx[k]] = x[idx[k]];
+    __threadfence_system();
+}
 __global__ void __launch_bounds__(SF3D_BLOCK) kern_unpack(double *__restrict__ x, const uint32_t *__restrict__ idx,
                                                           uint32_t n, const double *__restrict__ buf)
 {
@@ -834,7 +843,14 @@ static struct {
 } nccl;
 static ncclComm_t g_comm = nullptr;
 static int g_rank = 0, g_world = 1;
-struct HaloPeer { int peer; uint32_t nSend, nRecv; uint32_t *sendIdx, *recvIdx; double *sendBuf, *recvBuf; };
+struct HaloPeer {
+    int peer; uint32_t nSend, nRecv; uint32_t *sendIdx, *recvIdx; double *sendBuf, *recvBuf;
+    // direct mode: the neighbour's two solution buffers mapped through CUDA IPC, and where each of my
+    // send entries lives in the neighbour's numbering (its ghost row)
+    double *peerX[2]; uint32_t *remoteIdx;
+};
+static double *g_localX[2] = {nullptr, nullptr};     // this rank's x0 / x1 (exported to the neighbours)
+static bool g_directHalo = false;
 static std::vector<HaloPeer> g_halo;
 
 #define NCCL_OK(call)                                                                          \
@@ -885,9 +901,50 @@ int comm_world() { return g_world; }
 int comm_rank() { return g_rank; }
 void comm_clear_halo()
 {
-    for (HaloPeer &h : g_halo) { dev_free(h.sendIdx); dev_free(h.recvIdx); dev_free(h.sendBuf); dev_free(h.recvBuf); }
+    for (HaloPeer &h : g_halo)
+    {
+        dev_free(h.sendIdx); dev_free(h.recvIdx); dev_free(h.sendBuf); dev_free(h.recvBuf); dev_free(h.remoteIdx);
+        for (int b = 0; b < 2; ++b) if (h.peerX[b]) cudaIpcCloseMemHandle(h.peerX[b]);
+    }
     g_halo.clear();
+    g_directHalo = false;
 }
+// direct halo: export this rank's solution buffers / import a neighbour's
+void comm_ipc_export(double *x0, double *x1, unsigned char out[128])
+{
+    ensure_device();
+    cudaIpcMemHandle_t h0, h1;
+    CUDA_OK(cudaIpcGetMemHandle(&h0, x0));
+    CUDA_OK(cudaIpcGetMemHandle(&h1, x1));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(out, &h0, 64); memcpy(out + 64, &h1, 64);
+    g_localX[0] = x0; g_localX[1] = x1;
+}
+void comm_ipc_import(int peer, const unsigned char handles[128], uint32_t n, const uint32_t *remoteIdx)
+{
+    ensure_device();
+    for (HaloPeer &h : g_halo)
+    {
+        if (h.peer != peer) continue;
+        if (n != h.nSend) throw DeviceError{-1, "remote index list does not match the send list", "comm_ipc_import"};
+        cudaIpcMemHandle_t hh[2];
+        memcpy(&hh[0], handles, 64); memcpy(&hh[1], handles + 64, 64);
+        for (int b = 0; b < 2; ++b)
+        {
+            void *p = nullptr;
+            CUDA_OK(cudaIpcOpenMemHandle(&p, hh[b], cudaIpcMemLazyEnablePeerAccess));
+            h.peerX[b] = (double *)p;
+        }
+        h.remoteIdx = (uint32_t *)dev_alloc((size_t)n * 4);
+        if (n) h2d(h.remoteIdx, remoteIdx, (size_t)n * 4);
+        bool all = true;
+        for (HaloPeer &q : g_halo) if (!q.peerX[0] || !q.peerX[1]) all = false;
+        g_directHalo = all;
+        return;
+    }
+    throw DeviceError{-1, "unknown halo peer", "comm_ipc_import"};
+}
+bool comm_direct_halo() { return g_directHalo; }
 void comm_finalize()
 {
     comm_clear_halo();
@@ -897,7 +954,7 @@ void comm_finalize()
 void comm_add_halo_peer(int peer, uint32_t nSend, const uint32_t *sendIdx, uint32_t nRecv, const uint32_t *recvIdx)
 {
     HaloPeer h{};
-    h.peer = peer; h.nSend = nSend; h.nRecv = nRecv;
+    h.peer = peer; h.nSend = nSend; h.nRecv = nRecv; h.peerX[0] = h.peerX[1] = nullptr; h.remoteIdx = nullptr;
     h.sendIdx = (uint32_t *)dev_alloc((size_t)nSend * 4); h.recvIdx = (uint32_t *)dev_alloc((size_t)nRecv * 4);
     h.sendBuf = (double *)dev_alloc((size_t)nSend * 8); h.recvBuf = (double *)dev_alloc((size_t)nRecv * 8);
     if (nSend) h2d(h.sendIdx, sendIdx, (size_t)nSend * 4);
@@ -909,9 +966,18 @@ void comm_allreduce(double *devValues, int count, bool isMax)
     if (g_world <= 1) return;
     NCCL_OK(nccl.AllReduce(devValues, devValues, (size_t)count, NCCL_FLOAT64, isMax ? NCCL_MAX : NCCL_SUM, g_comm, g_stream));
 }
-void comm_halo(double *x)
+void comm_halo(double *x, const Ctrl *ctrl)
 {
     if (g_world <= 1 || g_halo.empty()) return;
+    if (g_directHalo)
+    {
+        // boundary rows go straight into the neighbours' ghost rows over NVLink (peer stores); the
+        // residual all-reduce that follows orders them before the next sweep on every rank
+        const int b = (x == g_localX[1]) ? 1 : 0;
+        for (HaloPeer &h : g_halo)
+            if (h.nSend) { kern_push<<<reduce_blocks(h.nSend), SF3D_BLOCK, 0, g_stream>>>(x, h.sendIdx, h.nSend, h.peerX[b], h.remoteIdx, ctrl); LAUNCH_CHECK(); }
+        return;
+    }
     for (HaloPeer &h : g_halo)
         if (h.nSend) { kern_pack<<<reduce_blocks(h.nSend), SF3D_BLOCK, 0, g_stream>>>(x, h.sendIdx, h.nSend, h.sendBuf); LAUNCH_CHECK(); }
     NCCL_OK(nccl.GroupStart());
@@ -986,7 +1052,7 @@ void k_jacobi(const SF3DView &v, const double *xin, double *xout, int maxIter, d
     if (v.world > 1)
     {
         ProfScope ps(SF3D_K_OTHER);
-        comm_halo(xout);                                 // boundary rows of x -> neighbours' ghost rows
+        comm_halo(xout, v.ctrl);                         // boundary rows of x -> neighbours' ghost rows
         comm_allreduce(v.ctrl->red, 1, false);           // residual sum over ranks
         kern_rule_jacobi<<<1, 1, 0, g_stream>>>(v.ctrl, v.nGlobal, maxIter, tol); LAUNCH_CHECK();
     }
@@ -1042,7 +1108,7 @@ void k_heat_jacobi(const SF3DView &v, const double *xin, double *xout, int maxIt
     kern_heat_jacobi<<<GRID(v.N)>>>(v, xin, xout, maxIter, tol); LAUNCH_CHECK();
     if (v.world > 1)
     {
-        comm_halo(xout);
+        comm_halo(xout, v.ctrl);
         comm_allreduce(v.ctrl->red, 1, true);
         kern_rule_heat_jacobi<<<1, 1, 0, g_stream>>>(v.ctrl, maxIter, tol); LAUNCH_CHECK();
     }
@@ -1056,7 +1122,7 @@ void k_heat_post(const SF3DView &v, const double *x, double dtHeat, double dtWat
 void k_heat_accept(const SF3DView &v, double dtHeat, double dtWater)
 { ProfScope ps(SF3D_K_OTHER); kern_heat_accept<<<GRID(v.N)>>>(v, dtHeat, dtWater); LAUNCH_CHECK(); }
 void k_heat_copy_T(const SF3DView &v, int mode) { kern_heat_copy_T<<<GRID(v.N)>>>(v, mode); LAUNCH_CHECK(); }
-void k_halo(double *x) { comm_halo(x); }
+void k_halo(double *x) { comm_halo(x, nullptr); }
 
 uint64_t k_count_links(const SF3DView &v)
 {

@@ -2,6 +2,8 @@
 broadcast through torch.distributed, slab catchment set up through the ordinary C ABI."""
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -30,5 +32,21 @@ def setup_slab(sf: SoilFluxes3D, rows: int, cols: int, n_soil_layers: int, rank:
     if world > 1:
         peers, send, recv = slab.halo()
         _ok(sf.set_halo(peers, send, recv, slab.n_global), "sf3d_ext_set_halo")
+        if os.environ.get("SF3D_DIRECT_HALO", "1") != "0":
+            wire_direct_halo(sf, slab, peers)
         _ok(sf.initializeBalance(), "initializeBalance")
     return slab, cat
+
+
+def wire_direct_halo(sf: SoilFluxes3D, slab: Slab, peers) -> None:
+    """Exchange the CUDA IPC handles of every rank's solution buffers and tell the library where each
+    send entry lives in the neighbour's numbering (= the neighbour's recv list towards this rank)."""
+    mine = torch.frombuffer(bytearray(sf.ipc_export()), dtype=torch.uint8).cuda()
+    gathered = [torch.empty_like(mine) for _ in range(slab.world)]
+    dist.all_gather(gathered, mine)
+    for p in peers:
+        other = make_slab(slab.rows, slab.cols, slab.layers - 1, slab.world, p)
+        o_peers, _o_send, o_recv = other.halo()
+        remote = o_recv[o_peers.index(slab.rank)]
+        _ok(sf.ipc_import(p, bytes(gathered[p].cpu().numpy().tobytes()), remote), "sf3d_ext_ipc_import")
+    dist.barrier()

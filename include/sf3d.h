@@ -277,6 +277,14 @@ uint8_t sf3d_ext_set_halo(uint32_t n_peers, const int32_t *peers,
                           const uint32_t *recv_count, const uint32_t *recv_idx,
                           uint64_t n_global_nodes);
 
+/* product only, optional after sf3d_ext_set_halo: direct halo.  Each rank exports CUDA IPC handles of
+ * its two solution buffers (128 bytes); a rank that imports its neighbours' handles, together with the
+ * position of each of its send entries in the neighbour's numbering (the neighbour's recv list),
+ * stores its boundary values straight into the neighbours' ghost rows through NVLink peer memory
+ * from a kernel that follows the sweep, instead of pack -> ncclSend/ncclRecv -> unpack. */
+uint8_t sf3d_ext_ipc_export(uint8_t handles[128]);
+uint8_t sf3d_ext_ipc_import(int peer, const uint8_t handles[128], uint32_t n, const uint32_t *remote_idx);
+
 /* product only: the cudaStream_t every kernel of the library is launched on (for CUDA-event
  * timing from the harness); NULL in the CPU libraries. */
 void *sf3d_ext_stream(void);
