@@ -355,11 +355,12 @@ template <bool HEAT>
 __global__ void __launch_bounds__(SF3D_BLOCK) kern_assemble(SF3DView v, double dt, int approx, double dtMin)
 {
     __shared__ double sh[SF3D_BLOCK / 32];
+    __shared__ double ksh[SF3D_NLINK * SF3D_BLOCK];          // ten conductances per thread, conflict-free layout
     double courant = 0.;
     for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
     {
         if (v.world > 1 && META_GHOST(v.meta[i])) continue;
-        const double c = sf3d_row_assemble<HEAT>(v, i, dt, approx);
+        const double c = sf3d_row_assemble<HEAT>(v, i, dt, approx, ksh + threadIdx.x, SF3D_BLOCK);
         courant = (courant < c) ? c : courant;
     }
     courant = block_reduce<true>(courant, sh);
