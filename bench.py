@@ -152,6 +152,7 @@ def main():
     ap.add_argument("--cols", type=int, default=WORKLOAD["cols"])
     ap.add_argument("--soil-layers", type=int, default=WORKLOAD["soil_layers"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--heat", action="store_true", help="config 3: coupled heat transport (not the headline workload)")
     args = ap.parse_args()
     warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -197,7 +198,7 @@ def main():
         slab, cat = setup_slab(sf, args.rows * world, args.cols, args.soil_layers, rank, world)
         n_owned = slab.n_owned
     else:
-        cat = Catchment(args.rows, args.cols, args.soil_layers)
+        cat = Catchment(args.rows, args.cols, args.soil_layers, heat=args.heat)
         setup(sf, cat)
         n_owned = cat.n_nodes
     N = cat.n_nodes
@@ -289,7 +290,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": f"C2 synthetic {args.rows}x{args.cols} DEM x (1+{args.soil_layers}) layers, "
-                            f"{RAIN_MM_H:g} mm/h storm hour, water only, Richards + Manning runoff",
+                            f"{RAIN_MM_H:g} mm/h storm hour, " + ("coupled heat (diffusive + latent)" if args.heat else "water only") + ", Richards + Manning runoff",
                 "nodes_per_gpu": N, "links_per_gpu": int(links),
                 "parallelism": "single GPU" if world == 1 else
                                f"{world} row slabs of {args.rows} DEM rows each (+1 ghost row per side), NCCL halo of x per sweep "
@@ -299,6 +300,7 @@ def main():
             },
             "sim_hours_per_wall_s": sim / 3600.0 / (ms * 1e-3),
             "sweeps": int(sweeps), "approximations": int(c1["approximations"] - c0["approximations"]),
+            "heat_steps": int(c1["heat_steps"] - c0["heat_steps"]), "heat_sweeps": int(c1["heat_sweeps"] - c0["heat_sweeps"]),
             "tries": int(c1["tries"] - c0["tries"]),
             "e2e": {"value": tot_iter_e2e / (ms_e2e * 1e-3), "unit": "node-iterations/s",
                     "h2d_bytes_per_step": 8 * N, "d2h_bytes_per_step": 8 * N,
