@@ -77,6 +77,7 @@ struct State {
            *partC = nullptr, *scratch = nullptr;
     uint32_t *mcol = nullptr;
     uint16_t *pid = nullptr; int32_t *pattern = nullptr; bool patternsOk = false;
+    uint32_t hotPid = 0; int32_t hotOff[SF3D_NLINK] = {0};
     Ctrl *ctrl = nullptr;
 
     Engine eng;
@@ -118,7 +119,8 @@ void fill_view()
     v.lidx = S.lidx.d; v.larea = S.larea.d; v.lflow = S.lflow.d; v.lgeom = S.lgeom;
     v.H = S.H.d; v.oldH = S.oldH.d; v.bestH = S.bestH; v.Se = S.Se.d; v.SeOld = S.SeOld; v.K = S.K.d;
     v.wFlow = S.wFlow; v.sink = S.sink.d; v.pond = S.pond.d; v.inv = nullptr;
-    v.mcol = S.mcol; v.pid = S.patternsOk ? S.pid : nullptr; v.pattern = S.patternsOk ? S.pattern : nullptr; v.mval = S.mval; v.b = S.b; v.cap = S.cap; v.x0 = S.x0; v.x1 = S.x1;
+    v.mcol = S.mcol; v.pid = S.patternsOk ? S.pid : nullptr; v.pattern = S.patternsOk ? S.pattern : nullptr; v.mval = S.mval;
+    v.hotPid = S.hotPid; memcpy(v.hotOff, S.hotOff, sizeof v.hotOff); v.b = S.b; v.cap = S.cap; v.x0 = S.x0; v.x1 = S.x1;
     v.soil = S.dSoil; v.rough = S.dRough;
     v.culverts = S.culverts.empty() ? nullptr : S.dCulv;
     v.culvertOf = S.culverts.empty() ? nullptr : S.culvertOf.d;
@@ -190,7 +192,7 @@ uint8_t sync_to_device(bool finalizeTopology = true)
         S.patternsOk = false;
         fill_view();
         k_link_geometry(S.eng.v, &ok);
-        S.patternsOk = k_build_patterns(S.eng.v, S.pid, S.pattern) && getenv("SF3D_EXPLICIT_INDEX") == nullptr;
+        S.patternsOk = k_build_patterns(S.eng.v, S.pid, S.pattern, &S.hotPid, S.hotOff) && getenv("SF3D_EXPLICIT_INDEX") == nullptr;
         fill_view();
         S.topoDirty = false;
         if (!ok)

@@ -284,6 +284,16 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_build_patterns(SF3DView v, un
         pid[i] = (uint16_t)slot;
     }
 }
+__global__ void __launch_bounds__(SF3D_BLOCK) kern_pattern_histogram(SF3DView v, const uint16_t *pid, unsigned int *count)
+{
+    for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
+    {
+        // one atomic per warp and distinct pattern (interior warps share a single pattern)
+        const unsigned p = pid[i];
+        const unsigned peers = __match_any_sync(__activemask(), p);
+        if ((__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&count[p], (unsigned)__popc(peers));
+    }
+}
 __global__ void __launch_bounds__(SF3D_BLOCK) kern_verify_patterns(SF3DView v, const int32_t *table, const uint16_t *pid, int *mismatch)
 {
     const size_t N = v.N;
@@ -1010,7 +1020,7 @@ void k_link_geometry(const SF3DView &v, int *surfaceOrderOk)
     dev_free(flag);
 }
 // returns true when the pattern-compressed index map reproduces mcol exactly
-bool k_build_patterns(const SF3DView &v, uint16_t *pid, int32_t *table)
+bool k_build_patterns(const SF3DView &v, uint16_t *pid, int32_t *table, uint32_t *hotPid, int32_t hotOff[SF3D_NLINK])
 {
     unsigned long long *keys = (unsigned long long *)dev_alloc(SF3D_PATTERN_SLOTS * sizeof(unsigned long long));
     int *flags = (int *)dev_alloc(2 * sizeof(int));
@@ -1019,7 +1029,16 @@ bool k_build_patterns(const SF3DView &v, uint16_t *pid, int32_t *table)
     kern_verify_patterns<<<GRID(v.N)>>>(v, table, pid, flags + 1); LAUNCH_CHECK();
     int h[2] = {1, 1};
     d2h(h, flags, sizeof h);
-    dev_free(keys); dev_free(flags);
+    // most frequent pattern -> kernel parameters
+    unsigned int *count = (unsigned int *)dev_alloc(SF3D_PATTERN_SLOTS * sizeof(unsigned int));
+    kern_pattern_histogram<<<GRID(v.N)>>>(v, pid, count); LAUNCH_CHECK();
+    std::vector<unsigned int> hc(SF3D_PATTERN_SLOTS);
+    d2h(hc.data(), count, hc.size() * sizeof(unsigned int));
+    uint32_t best = 0;
+    for (uint32_t k = 1; k < SF3D_PATTERN_SLOTS; ++k) if (hc[k] > hc[best]) best = k;
+    *hotPid = best;
+    d2h(hotOff, table + (size_t)best * SF3D_NLINK, SF3D_NLINK * sizeof(int32_t));
+    dev_free(keys); dev_free(flags); dev_free(count);
     return h[0] == 0 && h[1] == 0;
 }
 size_t pattern_table_bytes() { return (size_t)SF3D_PATTERN_SLOTS * SF3D_NLINK * sizeof(int32_t); }

@@ -399,15 +399,42 @@ SF3D_HD void sf3d_row_store(const SF3DView &v, uint32_t i, double dt, const doub
     v.b[i] = rhs * invDiag;                           // cpusolver.cpp:300
 }
 
-// linked node of matrix column c of row i: through the per-node link pattern when available
-// (2 bytes per node instead of 40), else through the explicit column-index array
-SF3D_HD uint32_t sf3d_col_index(const SF3DView &v, const int32_t *__restrict__ off, uint32_t i, int c)
+// linked nodes of the ten matrix columns of row i.  With pattern compression: the most frequent
+// pattern (interior nodes, > 95 % of a DEM catchment) comes from kernel parameters (no memory access at
+// all), other rows read their ten offsets from the small pattern table; without: the explicit array.
+SF3D_HD void sf3d_row_cols(const SF3DView &v, uint32_t i, uint32_t *j)
 {
-    return off ? (uint32_t)((int64_t)i + off[c]) : v.mcol[(size_t)c * v.N + i];
+    if (v.pid)
+    {
+        const uint32_t p = v.pid[i];
+        if (p == v.hotPid)
+        {
+            #pragma unroll
+            for (int c = 0; c < SF3D_NLINK; ++c) j[c] = (uint32_t)((int64_t)i + v.hotOff[c]);
+        }
+        else
+        {
+            const int32_t *off = v.pattern + (size_t)p * SF3D_NLINK;
+            #pragma unroll
+            for (int c = 0; c < SF3D_NLINK; ++c) j[c] = (uint32_t)((int64_t)i + off[c]);
+        }
+    }
+    else
+    {
+        #pragma unroll
+        for (int c = 0; c < SF3D_NLINK; ++c) j[c] = v.mcol[(size_t)c * v.N + i];
+    }
 }
+
+// assembly variant: one pointer to the row's ten offsets (fewer live registers than the branchy form,
+// and the assembly kernel is bound by fp64 issue, not by these L1-resident loads)
 SF3D_HD const int32_t *sf3d_row_pattern(const SF3DView &v, uint32_t i)
 {
     return v.pid ? v.pattern + (size_t)v.pid[i] * SF3D_NLINK : nullptr;
+}
+SF3D_HD uint32_t sf3d_col_index(const SF3DView &v, const int32_t *__restrict__ off, uint32_t i, int c)
+{
+    return off ? (uint32_t)((int64_t)i + off[c]) : v.mcol[(size_t)c * v.N + i];
 }
 
 // soil row: every link is a redistribution except an Up link to a surface node (infiltration).
@@ -499,14 +526,14 @@ SF3D_HD double sf3d_row_assemble(const SF3DView &v, uint32_t i, double dt, int a
 SF3D_HD double sf3d_row_jacobi(const SF3DView &v, uint32_t i, const double *__restrict__ xin, double *__restrict__ xout)
 {
     const size_t N = v.N;
-    const int32_t *off = sf3d_row_pattern(v, i);
+    uint32_t j[SF3D_NLINK];
+    sf3d_row_cols(v, i, j);
     double xnew = SF3D_LDS(v.b + i);
     #pragma unroll
     for (int c = 0; c < SF3D_NLINK; ++c)
     {
         const double A = SF3D_LDS(v.mval + (size_t)c * N + i);
-        const uint32_t j = sf3d_col_index(v, off, i, c);
-        xnew -= A * xin[j];
+        xnew -= A * xin[j[c]];
     }
     const double z = SF3D_LDS(v.z + i);
     if (i < v.Ns) xnew = sf3d_max(xnew, z);

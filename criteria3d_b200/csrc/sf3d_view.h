@@ -113,6 +113,8 @@ struct SF3DView {
     // (verified bit-exactly at finalize); null when the graph has too many distinct link patterns
     const uint16_t *pid;
     const int32_t *pattern;
+    uint32_t hotPid;                // the most frequent pattern (interior nodes) and its offsets, held in
+    int32_t hotOff[SF3D_NLINK];     // kernel parameters so that the common case needs no table load
     double *mval;
     double *b, *cap, *x0, *x1;
     // tables
