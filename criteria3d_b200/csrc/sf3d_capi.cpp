@@ -70,7 +70,7 @@ struct State {
                    hbSens, hbLat, hbRad, hbAdv, hbFixT, hbFixDepth;
     Mirror<double> lfluxes;               // [type][slot][node]; 1 type (HeatTotal) unless save mode All (9)
     int hfTypesAllocated = 0;
-    double *hFlux = nullptr, *lwFlux = nullptr, *lvFlux = nullptr, *hdiag = nullptr;
+    double *hFlux = nullptr, *lwFlux = nullptr, *lvFlux = nullptr, *hdiag = nullptr, *hTVK = nullptr, *hIVK = nullptr, *hCond = nullptr;
     // device-only
     double *bestH = nullptr, *SeOld = nullptr, *wFlow = nullptr, *lgeom = nullptr, *mval = nullptr,
            *b = nullptr, *cap = nullptr, *x0 = nullptr, *x1 = nullptr, *partA = nullptr, *partB = nullptr,
@@ -133,6 +133,7 @@ void fill_view()
         v.hbSens = S.hbSens.d; v.hbLat = S.hbLat.d; v.hbRad = S.hbRad.d; v.hbAdv = S.hbAdv.d;
         v.hbFixT = S.hbFixT.d; v.hbFixDepth = S.hbFixDepth.d;
         v.lwFlux = S.lwFlux; v.lvFlux = S.lvFlux; v.lfluxes = S.lfluxes.d; v.hdiag = S.hdiag;
+        v.hTVK = S.hTVK; v.hIVK = S.hIVK; v.hCond = S.hCond;
     }
 }
 
@@ -262,7 +263,7 @@ void release_all()
     S.T.release(); S.oldT.release(); S.hSink.release(); S.lfluxes.release();
     collect_heat_mirrors();
     for (Mirror<double> *m : heat_boundary_mirrors) m->release();
-    { double **hd[] = {&S.hFlux, &S.lwFlux, &S.lvFlux, &S.hdiag}; for (double **p : hd) { dev_free(*p); *p = nullptr; } }
+    { double **hd[] = {&S.hFlux, &S.lwFlux, &S.lvFlux, &S.hdiag, &S.hTVK, &S.hIVK, &S.hCond}; for (double **p : hd) { dev_free(*p); *p = nullptr; } }
     S.hfTypesAllocated = 0;
     double **devOnly[] = {&S.bestH, &S.SeOld, &S.wFlow, &S.lgeom, &S.mval, &S.b, &S.cap, &S.x0, &S.x1,
                           &S.partA, &S.partB, &S.partC, &S.scratch};
@@ -317,6 +318,7 @@ uint8_t sf3d_initialize(uint32_t nrNodes, uint32_t nrSurfaceNodes, uint8_t nrLat
             collect_heat_mirrors();
             for (Mirror<double> *m : heat_boundary_mirrors) m->alloc(N);
             S.hFlux = (double *)dev_alloc(N * 8); S.hdiag = (double *)dev_alloc(N * 8);
+            S.hTVK = (double *)dev_alloc(N * 8); S.hIVK = (double *)dev_alloc(N * 8); S.hCond = (double *)dev_alloc(N * 8);
             S.lwFlux = (double *)dev_alloc(L * 8); S.lvFlux = (double *)dev_alloc(L * 8);
             S.hfTypesAllocated = (S.hfMode == 2) ? 9 : 1;
             S.lfluxes.alloc((size_t)S.hfTypesAllocated * L);

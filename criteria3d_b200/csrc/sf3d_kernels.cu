@@ -688,6 +688,11 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_update_conductance(SF3DView v
     for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
         sf3d_row_update_conductance(v, i);
 }
+__global__ void __launch_bounds__(SF3D_BLOCK) kern_heat_coeffs(SF3DView v, double dtHeat, double dtWater)
+{
+    for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
+        sf3d_row_heat_coeffs(v, i, dtHeat, dtWater);
+}
 __global__ void __launch_bounds__(SF3D_BLOCK) kern_save_water_fluxes(SF3DView v, double dtHeat, double dtWater)
 {
     for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
@@ -1110,7 +1115,11 @@ void k_build_grid(const SF3DView &v, const GridDev &g)
 
 void k_update_conductance(const SF3DView &v) { ProfScope ps(SF3D_K_OTHER); kern_update_conductance<<<GRID(v.N)>>>(v); LAUNCH_CHECK(); }
 void k_save_water_fluxes(const SF3DView &v, double dtHeat, double dtWater)
-{ ProfScope ps(SF3D_K_OTHER); kern_save_water_fluxes<<<GRID(v.N)>>>(v, dtHeat, dtWater); LAUNCH_CHECK(); }
+{
+    ProfScope ps(SF3D_K_OTHER);
+    kern_heat_coeffs<<<GRID(v.N)>>>(v, dtHeat, dtWater); LAUNCH_CHECK();
+    kern_save_water_fluxes<<<GRID(v.N)>>>(v, dtHeat, dtWater); LAUNCH_CHECK();
+}
 void k_reset_water_fluxes(const SF3DView &v) { if (v.hfSaveMode == 2) { kern_reset_water_fluxes<<<GRID(v.N)>>>(v); LAUNCH_CHECK(); } }
 void k_boundary_heat(const SF3DView &v, double maxTimeStep)
 {
@@ -1119,7 +1128,11 @@ void k_boundary_heat(const SF3DView &v, double maxTimeStep)
     if (v.world > 1) { comm_allreduce(v.ctrl->red, 1, true); kern_rule_heat_courant<<<1, 1, 0, g_stream>>>(v.ctrl); LAUNCH_CHECK(); }
 }
 void k_heat_begin(const SF3DView &v, double dtHeat, double dtWater)
-{ ProfScope ps(SF3D_K_OTHER); kern_heat_begin<<<GRID(v.N)>>>(v, dtHeat, dtWater); LAUNCH_CHECK(); }
+{
+    ProfScope ps(SF3D_K_OTHER);
+    kern_heat_begin<<<GRID(v.N)>>>(v, dtHeat, dtWater); LAUNCH_CHECK();
+    kern_heat_coeffs<<<GRID(v.N)>>>(v, dtHeat, dtWater); LAUNCH_CHECK();
+}
 void k_heat_assemble(const SF3DView &v, double dtHeat, double dtWater)
 { ProfScope ps(SF3D_K_OTHER); kern_heat_assemble<<<GRID(v.N)>>>(v, dtHeat, dtWater); LAUNCH_CHECK(); }
 void k_heat_jacobi(const SF3DView &v, const double *xin, double *xout, int maxIter, double tol)

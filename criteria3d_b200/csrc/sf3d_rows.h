@@ -147,6 +147,7 @@ SF3D_HD void sf3d_row_restore_old(const SF3DView &v, uint32_t i) { v.H[i] = v.ol
 // Heat hooks (vapour conductivity, HeatSurface evaporation) live in sf3d_rows_heat.h.
 // ==========================================================================================
 SF3D_HD double sf3d_heat_vapor_K(const SF3DView &v, uint32_t i);                       // soilPhysics.cpp:168-169
+SF3D_HD double sf3d_heat_water_tvk(const SF3DView &v, uint32_t i);
 SF3D_HD double sf3d_heat_dthetav_dh(const SF3DView &v, uint32_t i, double dThetadH);     // soilPhysics.cpp:287-299
 SF3D_HD double sf3d_heat_surface_boundary(const SF3DView &v, uint32_t i, double dt, double *upExtra);
 SF3D_HD double sf3d_heat_surface_pull(const SF3DView &v, uint32_t i, double dt, int *active);
@@ -198,6 +199,7 @@ SF3D_HD void sf3d_row_node_phase(const SF3DView &v, uint32_t i, double dt, int w
         K = sf3d_mualem(s, v.wrcModel, Se);
         if (HEAT && v.computeHeatVapor) K += sf3d_heat_vapor_K(v, i);
         v.K[i] = K;
+        if (HEAT && v.computeHeatVapor) v.hTVK[i] = sf3d_heat_water_tvk(v, i);     // read by both ends of every link
         if (withCapacity)
         {
             const double dThetadH = sf3d_dtheta_dh(s, v.wrcModel, H, oldH, z, Se, v.SeOld[i]);

@@ -189,6 +189,22 @@ SF3D_HD double sf3d_heat_dthetav_dh(const SF3DView &v, uint32_t i, double dTheta
     return dThetaVdPsi * HC_GRAVITY;
 }
 
+// per-node thermal vapour conductivity with the processType::Water arguments (mean temperature,
+// current matric potential): stored by the node phase, read by both ends of every link in the assembly
+SF3D_HD double sf3d_heat_water_tvk(const SF3DView &v, uint32_t i)
+{ return h_thermal_vapor_conductivity(v, i, h_mean_T(v, i), v.H[i] - v.z[i]); }
+// per-node coefficients with the processType::Heat arguments (node temperature, head averaged over the
+// heat sub-step): stored by sf3d_row_heat_coeffs before the flux snapshot and before every heat assembly
+SF3D_HD void sf3d_row_heat_coeffs(const SF3DView &v, uint32_t i, double dtHeat, double dtWater)
+{
+    if (i < v.Ns) return;
+    const double avgH = (h_H_from_steps(v, i, dtHeat, dtWater) + v.oldH[i]) * 0.5 - v.z[i];
+    const double T = v.T[i];
+    v.hCond[i] = h_soil_heat_conductivity(v, i, T, avgH);
+    v.hIVK[i] = h_isothermal_vapor_conductivity(v, i, T, avgH);
+    v.hTVK[i] = h_thermal_vapor_conductivity(v, i, T, avgH);
+}
+
 // computeThermalLiquidFlux / computeThermalVaporFlux (heat.cpp:458-553); forWater selects the
 // processType::Water branch (mean temperatures, current heads) or the Heat branch
 SF3D_HD void h_thermal_operands(const SF3DView &v, uint32_t i, uint32_t j, bool forWater, bool liquid, double dtHeat, double dtWater,
@@ -224,12 +240,15 @@ SF3D_HD double h_thermal_liquid_flux(const SF3DView &v, uint32_t i, int slot, ui
     const double density = avg * (dstT - srcT) / h_distance3d(v, i, j);
     return density * v.larea[(size_t)slot * v.N + i];
 }
-SF3D_HD double h_thermal_vapor_flux(const SF3DView &v, uint32_t i, int slot, uint32_t j, bool forWater, double dtHeat, double dtWater)
+// usePre: the two conductivities were stored per node (v.hTVK) by the pass that precedes the caller,
+// evaluated with exactly the arguments computed here
+SF3D_HD double h_thermal_vapor_flux(const SF3DView &v, uint32_t i, int slot, uint32_t j, bool forWater, double dtHeat, double dtWater,
+                                   bool usePre = false)
 {
     double srcT, dstT, srcH, dstH;
     h_thermal_operands(v, i, j, forWater, false, dtHeat, dtWater, srcT, dstT, srcH, dstH);
-    const double a = h_thermal_vapor_conductivity(v, i, srcT, srcH);
-    const double b = h_thermal_vapor_conductivity(v, j, dstT, dstH);
+    const double a = usePre ? v.hTVK[i] : h_thermal_vapor_conductivity(v, i, srcT, srcH);
+    const double b = usePre ? v.hTVK[j] : h_thermal_vapor_conductivity(v, j, dstT, dstH);
     const double avg = sf3d_mean(a, b, 2);
     const double density = avg * (dstT - srcT) / h_distance3d(v, i, j);
     return density * v.larea[(size_t)slot * v.N + i];
@@ -238,7 +257,7 @@ SF3D_HD double h_thermal_vapor_flux(const SF3DView &v, uint32_t i, int slot, uin
 SF3D_HD double sf3d_heat_thermal_invariant(const SF3DView &v, uint32_t i, int slot, uint32_t j)
 {
     double f = h_thermal_liquid_flux(v, i, slot, j, true, 0., 0.);
-    if (v.computeHeatVapor) f += h_thermal_vapor_flux(v, i, slot, j, true, 0., 0.) / HC_WATER_DENSITY;
+    if (v.computeHeatVapor) f += h_thermal_vapor_flux(v, i, slot, j, true, 0., 0., true) / HC_WATER_DENSITY;
     return f;
 }
 
@@ -355,8 +374,8 @@ SF3D_HD double h_isothermal_vapor_flux(const SF3DView &v, uint32_t i, int slot, 
 {
     const double srcH = (h_H_from_steps(v, i, dtHeat, dtWater) + v.oldH[i]) * 0.5 - v.z[i];
     const double dstH = (h_H_from_steps(v, j, dtHeat, dtWater) + v.oldH[j]) * 0.5 - v.z[j];
-    const double a = h_isothermal_vapor_conductivity(v, i, v.T[i], srcH);
-    const double b = h_isothermal_vapor_conductivity(v, j, v.T[j], dstH);
+    const double a = v.hIVK[i];          // = computeNodeIsothermalVaporConductivity(i, T[i], srcH), see sf3d_row_heat_coeffs
+    const double b = v.hIVK[j];
     const double avg = sf3d_mean(a, b, 2);
     const double srcPsi = srcH * HC_GRAVITY, dstPsi = dstH * HC_GRAVITY;
     const double deltaPsi = dstPsi - srcPsi;
@@ -379,7 +398,7 @@ SF3D_HD void sf3d_row_save_water_fluxes(const SF3DView &v, uint32_t i, double dt
         const bool deep = !(i < v.Ns) && !(j < v.Ns);
         const double isoVapor = deep ? h_isothermal_vapor_flux(v, i, slot, j, dtHeat, dtWater) : 0.;
         const double thLiquid = deep ? h_thermal_liquid_flux(v, i, slot, j, false, dtHeat, dtWater) : 0.;
-        const double thVapor = deep ? h_thermal_vapor_flux(v, i, slot, j, false, dtHeat, dtWater) : 0.;
+        const double thVapor = deep ? h_thermal_vapor_flux(v, i, slot, j, false, dtHeat, dtWater, true) : 0.;
         v.lwFlux[li] = (double)(float)(isoLiquid - isoVapor / HC_WATER_DENSITY + thLiquid);
         v.lvFlux[li] = (double)(float)(isoVapor + thVapor);
         if (v.hfSaveMode == 2)
@@ -490,10 +509,9 @@ SF3D_HD void h_save_specific_flux(const SF3DView &v, uint32_t i, int slot, int t
 SF3D_HD double h_conduction(const SF3DView &v, uint32_t i, int slot, uint32_t j, double dtHeat, double dtWater)
 {
     const double zeta = v.larea[(size_t)slot * v.N + i] / h_distance3d(v, i, j);
-    const double nodeAvgH = (h_H_from_steps(v, i, dtHeat, dtWater) + v.oldH[i]) * 0.5 - v.z[i];
-    const double linkAvgH = (h_H_from_steps(v, j, dtHeat, dtWater) + v.oldH[j]) * 0.5 - v.z[j];
-    const double nodeK = h_soil_heat_conductivity(v, i, v.T[i], nodeAvgH);
-    const double linkK = h_soil_heat_conductivity(v, j, v.T[j], linkAvgH);
+    (void)dtHeat; (void)dtWater;
+    const double nodeK = v.hCond[i];     // = computeNodeHeatSoilConductivity(i, T[i], avgH_i), see sf3d_row_heat_coeffs
+    const double linkK = v.hCond[j];
     return zeta * sf3d_mean(nodeK, linkK, 2);
 }
 // computeAdvectiveFlux (heat.cpp:606-621)
@@ -635,7 +653,7 @@ SF3D_HD void sf3d_row_heat_accept(const SF3DView &v, uint32_t i, double dtHeat, 
             {
                 if (v.computeHeatVapor)
                 {
-                    const double thLatent = h_thermal_vapor_flux(v, i, slot, j, false, dtHeat, dtWater) * h_latent_vaporization(v.T[i] - HC_ZEROCELSIUS);
+                    const double thLatent = h_thermal_vapor_flux(v, i, slot, j, false, dtHeat, dtWater, false) * h_latent_vaporization(v.T[i] - HC_ZEROCELSIUS);
                     h_save_specific_flux(v, i, slot, 3, thLatent);
                     heatDiff -= thLatent;
                 }

@@ -129,6 +129,9 @@ struct SF3DView {
     double *lwFlux, *lvFlux;        // per link, slot-major (float-rounded values, heat.cpp:126-127)
     double *lfluxes;                // [type][slot][i], types allocated per hfSaveMode
     double *hdiag;                  // heat matrix diagonal (kept, cpusolver.cpp:561-567)
+    // per-node coefficients the reference re-evaluates for both ends of every link (same arguments, same
+    // value): thermal / isothermal vapour conductivity and soil heat conductivity, computed once per node
+    double *hTVK, *hIVK, *hCond;
     // control / reduction scratch
     Ctrl *ctrl;
     double *partA, *partB, *partC;  // per-block partials
