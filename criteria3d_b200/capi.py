@@ -247,6 +247,8 @@ _EXT = [
     ("sf3d_ext_backend", C.c_char_p, []),
     ("sf3d_ext_set_device", u8, [cint]),
     ("sf3d_ext_reset_solver", u8, []),
+    ("sf3d_ext_jacobi_sweep", u8, [u32, u32, C.POINTER(u8), C.POINTER(u32), C.POINTER(dbl), C.POINTER(dbl), C.POINTER(dbl),
+                                   C.POINTER(dbl), C.POINTER(dbl), C.POINTER(dbl)]),
     ("sf3d_ext_comm_unique_id", u8, [C.POINTER(u8)]),
     ("sf3d_ext_comm_init", u8, [cint, cint, C.POINTER(u8)]),
     ("sf3d_ext_comm_finalize", u8, []),
@@ -372,6 +374,20 @@ class SoilFluxes3D:
         ri = np.ascontiguousarray(np.concatenate(recv_lists) if len(recv_lists) else np.zeros(0), dtype=np.uint32)
         return self.lib.sf3d_ext_set_halo(len(peers_a), _ptr(peers_a, C.c_int32), _ptr(sc, u32), _ptr(si, u32),
                                           _ptr(rc_, u32), _ptr(ri, u32), int(n_global_nodes))
+
+    def jacobi_sweep(self, n_surface, ncols, col, val, b, z, x_in):
+        """one sweep on a system in the reference's compact row layout; returns (x_out, norm)"""
+        n = len(b)
+        ncols = np.ascontiguousarray(ncols, np.uint8); col = np.ascontiguousarray(col, np.uint32)
+        val = np.ascontiguousarray(val, np.float64); b = np.ascontiguousarray(b, np.float64)
+        z = np.ascontiguousarray(z, np.float64); x_in = np.ascontiguousarray(x_in, np.float64)
+        x_out = np.empty(n, np.float64)
+        norm = dbl(0.0)
+        rc = self.lib.sf3d_ext_jacobi_sweep(n, n_surface, _ptr(ncols, u8), _ptr(col, u32), _ptr(val, dbl), _ptr(b, dbl),
+                                            _ptr(z, dbl), _ptr(x_in, dbl), _ptr(x_out, dbl), C.byref(norm))
+        if rc:
+            raise RuntimeError(f"sf3d_ext_jacobi_sweep -> {SF3Derror(rc).name}")
+        return x_out, norm.value
 
     def reset_solver(self) -> int:
         return self.lib.sf3d_ext_reset_solver()

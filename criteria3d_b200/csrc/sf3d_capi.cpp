@@ -1125,6 +1125,45 @@ uint8_t sf3d_ext_set_device(int device)
 
 uint8_t sf3d_ext_reset_solver(void) { g_params = default_params(); return SF3D_OK; }
 
+uint8_t sf3d_ext_jacobi_sweep(uint32_t n, uint32_t nSurface, const uint8_t *ncols, const uint32_t *col, const double *val,
+                              const double *b, const double *z, const double *xIn, double *xOut, double *norm)
+{
+    if (!ncols || !col || !val || !b || !z || !xIn || !xOut || !norm || n == 0) return SF3D_PARAMETER_ERROR;
+    return guarded([&]() -> uint8_t {
+        dev_select(g_device);
+        // compact rows -> the product's fixed ten-column layout, column order preserved; absent entries 0 / self
+        std::vector<double> mv((size_t)SF3D_NLINK * n, 0.0);
+        std::vector<uint32_t> mc((size_t)SF3D_NLINK * n);
+        for (uint32_t r = 0; r < n; ++r)
+            for (int c = 0; c < SF3D_NLINK; ++c)
+            {
+                const bool has = (c + 1) < ncols[r];
+                mv[(size_t)c * n + r] = has ? val[(size_t)r * 11 + c + 1] : 0.0;
+                mc[(size_t)c * n + r] = has ? col[(size_t)r * 11 + c + 1] : r;
+            }
+        SF3DView v{};
+        v.N = n; v.Ns = nSurface; v.world = 1; v.nGlobal = (double)n;
+        double *dmv = (double *)dev_alloc(mv.size() * 8); uint32_t *dmc = (uint32_t *)dev_alloc(mc.size() * 4);
+        double *db = (double *)dev_alloc((size_t)n * 8), *dz = (double *)dev_alloc((size_t)n * 8);
+        double *dx0 = (double *)dev_alloc((size_t)n * 8), *dx1 = (double *)dev_alloc((size_t)n * 8);
+        const size_t nb = (size_t)reduce_blocks(0xFFFFFFFFu);
+        double *part = (double *)dev_alloc(nb * 8);
+        Ctrl *ctrl = (Ctrl *)dev_alloc(sizeof(Ctrl));
+        h2d(dmv, mv.data(), mv.size() * 8); h2d(dmc, mc.data(), mc.size() * 4);
+        h2d(db, b, (size_t)n * 8); h2d(dz, z, (size_t)n * 8); h2d(dx0, xIn, (size_t)n * 8);
+        v.mval = dmv; v.mcol = dmc; v.b = db; v.z = dz; v.ctrl = ctrl; v.partA = part; v.pid = nullptr; v.pattern = nullptr;
+        Ctrl c0{}; c0.status = SOLVE_RUNNING; c0.bestNorm = 1.;
+        write_ctrl(v, &c0);
+        k_jacobi(v, dx0, dx1, 1000000, 0.0);
+        Ctrl c1{};
+        read_ctrl(v, &c1);
+        d2h(xOut, dx1, (size_t)n * 8);
+        *norm = c1.lastNorm;
+        for (void *p : {(void *)dmv, (void *)dmc, (void *)db, (void *)dz, (void *)dx0, (void *)dx1, (void *)part, (void *)ctrl}) dev_free(p);
+        return SF3D_OK;
+    }, (uint8_t)SF3D_SOLVER_ERROR);
+}
+
 uint8_t sf3d_ext_comm_unique_id(uint8_t id[128])
 { return guarded([&]() -> uint8_t { dev_select(g_device); comm_unique_id(id); return SF3D_OK; }, (uint8_t)SF3D_SOLVER_ERROR); }
 uint8_t sf3d_ext_comm_init(int rank, int world, const uint8_t id[128])

@@ -250,6 +250,15 @@ typedef struct sf3d_counters {
 uint8_t sf3d_ext_get_counters(sf3d_counters *out);
 uint8_t sf3d_ext_reset_counters(void);
 
+/* Known-answer entry for the hot kernel: ONE Jacobi sweep (Water::JacobiWaterCPU, water.cpp:565-601) on a
+ * caller-supplied system in the reference's compact row layout (MatrixCPU, types_cpu.h:7-13: per row
+ * ncols[r] entries, entry 0 = diagonal, then the stored off-diagonals; 11 slots per row).  Rows
+ * [0, n_surface) are clamped to x >= z.  Writes x_out and returns the mean norm in *norm.  Independent of
+ * the global instance.  The CPU libraries implement it with their own sweep. */
+uint8_t sf3d_ext_jacobi_sweep(uint32_t n, uint32_t n_surface, const uint8_t *ncols, const uint32_t *col,
+                              const double *val, const double *b, const double *z, const double *x_in,
+                              double *x_out, double *norm);
+
 /* name/version of the implementation behind the ABI ("b200", "oracle", "reference") */
 const char *sf3d_ext_backend(void);
 

@@ -274,6 +274,29 @@ uint8_t sf3d_ext_set_halo(uint32_t n, const int32_t *p, const uint32_t *sc, cons
 void *sf3d_ext_stream(void) { return nullptr; }
 uint8_t sf3d_ext_profile(int) { return SF3D_PARAMETER_ERROR; }
 uint8_t sf3d_ext_get_kernel_times(sf3d_kernel_times *) { return SF3D_PARAMETER_ERROR; }
+uint8_t sf3d_ext_jacobi_sweep(uint32_t n, uint32_t ns, const uint8_t *ncols, const uint32_t *col, const double *val,
+                              const double *b, const double *z, const double *x_in, double *x_out, double *norm)
+{
+    /* the REAL Water::JacobiWaterCPU on temporary MatrixCPU / VectorCPU objects; it reads nodeGrid.z and
+       nodeGrid.nrSurfaceNodes, which are pointed at the caller's data for the duration of the call */
+    if (!ncols || !col || !val || !b || !z || !x_in || !x_out || !norm || n == 0) return SF3D_PARAMETER_ERROR;
+    if (!sf::solver) return SF3D_MEMORY_ERROR;          /* __ompStatus dereferences the solver */
+    std::vector<uint32_t *> colp(n); std::vector<double *> valp(n);
+    std::vector<uint32_t> colc(col, col + (size_t)n * 11); std::vector<double> valc(val, val + (size_t)n * 11);
+    for (uint32_t r = 0; r < n; ++r) { colp[r] = &colc[(size_t)r * 11]; valp[r] = &valc[(size_t)r * 11]; }
+    std::vector<uint8_t> nc(ncols, ncols + n);
+    std::vector<double> x(x_in, x_in + n), xn(n, 0.0), bb(b, b + n);
+    sf::MatrixCPU A; A.numRows = n; A.numColsInRow = nc.data(); A.columnIndeces = colp.data(); A.values = valp.data();
+    sf::VectorCPU vx{n, x.data()}, vxn{n, xn.data()}, vb{n, bb.data()};
+    double *saveZ = sf::nodeGrid.z; uint32_t saveNs = sf::nodeGrid.nrSurfaceNodes;
+    sf::nodeGrid.z = const_cast<double *>(z); sf::nodeGrid.nrSurfaceNodes = ns;
+    const uint64_t sweeps = g_cnt.sweeps;
+    *norm = __wrap__ZN12soilFluxes3D2v25Water14JacobiWaterCPUERNS0_9VectorCPUES3_RKNS0_9MatrixCPUERKS2_(vx, vxn, A, vb);
+    g_cnt.sweeps = sweeps;
+    sf::nodeGrid.z = saveZ; sf::nodeGrid.nrSurfaceNodes = saveNs;
+    std::memcpy(x_out, vx.values, (size_t)n * sizeof(double));      /* the function swaps the two vectors */
+    return SF3D_OK;
+}
 uint8_t sf3d_ext_reset_solver(void)
 {
     /* every field of SolverParameters back to its default (types.h:291-315); deltaTcurr = NODATA

@@ -29,8 +29,37 @@ def config1_inputs():
                         cell=np.float64(dem.cell), xll=np.float64(dem.xll), yll=np.float64(dem.yll))
 
 
+def jacobi_kat(ref):
+    """linear systems captured from inside the reference (the matrix JacobiWaterCPU actually sees, compact
+    rows with dropped zero conductances) -> tests/golden/jacobi_kat.npz"""
+    import ctypes as C
+    from criteria3d_b200.synth import Catchment, run_hours, setup
+    lib = ref.lib
+    lib.sf3d_ref_captured_rows.restype = C.c_uint32
+    lib.sf3d_ref_captured_norm.restype = C.c_double
+    cat = Catchment(14, 11, 4)
+    setup(ref, cat, threads=1)
+    lib.sf3d_ref_capture_jacobi(1)
+    out = {}
+    for k, mm in enumerate((25.0, 40.0)):
+        run_hours(ref, cat, [mm], max_steps=6 + 5 * k)
+        n = lib.sf3d_ref_captured_rows()
+        ncols = np.empty(n, np.uint8); col = np.empty(n * 11, np.uint32); val = np.empty(n * 11, np.float64)
+        b = np.empty(n); x_in = np.empty(n); x_out = np.empty(n)
+        P = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+        lib.sf3d_ref_captured_copy(P(ncols, C.c_uint8), P(col, C.c_uint32), P(val, C.c_double), P(b, C.c_double),
+                                   P(x_in, C.c_double), P(x_out, C.c_double))
+        z = ref.get_field(4, 0, n) - ref.get_field(3, 0, n)          # H - psi
+        out.update({f"ncols{k}": ncols, f"col{k}": col, f"val{k}": val, f"b{k}": b, f"z{k}": z, f"x_in{k}": x_in,
+                    f"x_out{k}": x_out, f"norm{k}": np.float64(lib.sf3d_ref_captured_norm()), f"ns{k}": np.int64(cat.n_surface)})
+    lib.sf3d_ref_capture_jacobi(0)
+    np.savez_compressed(Path(__file__).parent / "jacobi_kat.npz", **out)
+    print("jacobi_kat: 2 systems of", n, "rows")
+
+
 def main():
     config1_inputs()
+    jacobi_kat(SoilFluxes3D(REFERENCE_LIB))
     ref = SoilFluxes3D(REFERENCE_LIB)
     assert ref.backend == "reference"
     for name, fn in sorted({**SCENARIOS, **HEAT_SCENARIOS}.items()):
