@@ -254,6 +254,8 @@ _EXT = [
     ("sf3d_ext_comm_finalize", u8, []),
     ("sf3d_ext_ipc_export", u8, [C.POINTER(u8)]),
     ("sf3d_ext_ipc_import", u8, [cint, C.POINTER(u8), u32, C.POINTER(u32)]),
+    ("sf3d_ext_mailbox_export", u8, [C.POINTER(u8)]),
+    ("sf3d_ext_mailbox_import", u8, [cint, C.POINTER(u8)]),
     ("sf3d_ext_set_halo", u8, [u32, C.POINTER(C.c_int32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32),
                                C.POINTER(u32), C.c_uint64]),
     ("sf3d_ext_stream", C.c_void_p, []),
@@ -362,6 +364,16 @@ class SoilFluxes3D:
         buf = (u8 * 128).from_buffer_copy(handles)
         r = np.ascontiguousarray(remote_idx, dtype=np.uint32)
         return self.lib.sf3d_ext_ipc_import(peer, buf, r.size, _ptr(r, u32))
+
+    def mailbox_export(self) -> bytes:
+        buf = (u8 * 64)()
+        rc = self.lib.sf3d_ext_mailbox_export(buf)
+        if rc:
+            raise RuntimeError(f"sf3d_ext_mailbox_export -> {SF3Derror(rc).name}")
+        return bytes(buf)
+
+    def mailbox_import(self, peer: int, handle: bytes) -> int:
+        return self.lib.sf3d_ext_mailbox_import(peer, (u8 * 64).from_buffer_copy(handle))
 
     def comm_finalize(self) -> int:
         return self.lib.sf3d_ext_comm_finalize()

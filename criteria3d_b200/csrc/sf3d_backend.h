@@ -38,7 +38,9 @@ int  comm_world();
 int  comm_rank();
 void comm_clear_halo();
 void comm_add_halo_peer(int peer, uint32_t nSend, const uint32_t *sendIdx, uint32_t nRecv, const uint32_t *recvIdx);
-void comm_allreduce(double *devValues, int count, bool isMax);
+void comm_allreduce(double *devValues, int count, bool isMax, Ctrl *ctrl);
+void comm_mailbox_export(unsigned char out[64]);
+void comm_mailbox_import(int peer, const unsigned char handle[64]);
 void comm_halo(double *x, const Ctrl *ctrl);
 void comm_ipc_export(double *x0, double *x1, unsigned char out[128]);
 void comm_ipc_import(int peer, const unsigned char handles[128], uint32_t n, const uint32_t *remoteIdx);

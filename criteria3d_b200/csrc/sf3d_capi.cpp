@@ -1184,6 +1184,13 @@ uint8_t sf3d_ext_ipc_import(int peer, const uint8_t handles[128], uint32_t n, co
         return SF3D_OK;
     }, (uint8_t)SF3D_SOLVER_ERROR);
 }
+uint8_t sf3d_ext_mailbox_export(uint8_t handle[64])
+{ return guarded([&]() -> uint8_t { dev_select(g_device); comm_mailbox_export(handle); return SF3D_OK; }, (uint8_t)SF3D_SOLVER_ERROR); }
+uint8_t sf3d_ext_mailbox_import(int peer, const uint8_t handle[64])
+{
+    if (!handle) return SF3D_PARAMETER_ERROR;
+    return guarded([&]() -> uint8_t { comm_mailbox_import(peer, handle); return SF3D_OK; }, (uint8_t)SF3D_SOLVER_ERROR);
+}
 uint8_t sf3d_ext_comm_finalize(void)
 { return guarded([&]() -> uint8_t { comm_finalize(); return SF3D_OK; }, (uint8_t)SF3D_SOLVER_ERROR); }
 uint8_t sf3d_ext_set_halo(uint32_t nPeers, const int32_t *peers, const uint32_t *sendCount, const uint32_t *sendIdx,
@@ -1208,6 +1215,7 @@ uint8_t sf3d_ext_set_halo(uint32_t nPeers, const int32_t *peers, const uint32_t 
             so += sendCount[p]; ro += recvCount[p];
         }
         S.nGlobal = (double)nGlobalNodes;
+        S.topoDirty = true;                     // ghost rows get their reserved pattern id at the next finalize
         return SF3D_OK;
     }, (uint8_t)SF3D_SOLVER_ERROR);
 }

@@ -238,6 +238,7 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_link_geometry(SF3DView v, int
 // proves  i + pattern[pid[i]][c] == mcol[c][i]  for every entry (bit-exact integer map) or the
 // explicit index array stays in use.
 #define SF3D_PATTERN_SLOTS 1024
+#define SF3D_GHOST_PID 0xFFFFu      // rows received from a neighbouring slab: never swept
 __device__ __forceinline__ unsigned long long pattern_hash(const int32_t *off)
 {
     unsigned long long h = 0x9E3779B97F4A7C15ull;
@@ -255,6 +256,7 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_build_patterns(SF3DView v, un
     const size_t N = v.N;
     for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
     {
+        if (v.world > 1 && META_GHOST(v.meta[i])) { pid[i] = SF3D_GHOST_PID; continue; }
         int32_t off[SF3D_NLINK];
         bool fits = true;
         #pragma unroll
@@ -290,6 +292,7 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_pattern_histogram(SF3DView v,
     {
         // one atomic per warp and distinct pattern (interior warps share a single pattern)
         const unsigned p = pid[i];
+        if (p == SF3D_GHOST_PID) continue;
         const unsigned peers = __match_any_sync(__activemask(), p);
         if ((__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&count[p], (unsigned)__popc(peers));
     }
@@ -299,6 +302,7 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_verify_patterns(SF3DView v, c
     const size_t N = v.N;
     for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
     {
+        if (pid[i] == SF3D_GHOST_PID) { if (!(v.world > 1 && META_GHOST(v.meta[i]))) *mismatch = 1; continue; }
         const int32_t *off = table + (size_t)pid[i] * SF3D_NLINK;
         #pragma unroll
         for (int c = 0; c < SF3D_NLINK; ++c)
@@ -397,7 +401,7 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_jacobi(SF3DView v, const doub
     double norm = 0.;
     for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
     {
-        if (v.world > 1 && META_GHOST(v.meta[i])) continue;
+        if (v.world > 1 && (v.pid ? (v.pid[i] == SF3D_GHOST_PID) : (META_GHOST(v.meta[i]) != 0))) continue;
         norm += sf3d_row_jacobi(v, i, xin, xout);
     }
     norm = block_reduce<false>(norm, sh);
@@ -420,6 +424,45 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_pack(const double *__restrict
 {
     for (uint32_t k = blockIdx.x * SF3D_BLOCK + threadIdx.x; k < n; k += gridDim.x * SF3D_BLOCK) buf[k] = x[idx[k]];
 }
+// All-reduce of up to four doubles over peer memory, one warp per rank: lane r stores this rank's values
+// and then the sequence number into rank r's mailbox (NVLink peer stores, system-scope fence in between),
+// then waits until rank r's contribution for the same sequence number has landed in the local mailbox;
+// lane 0 folds the contributions in rank order, so every rank obtains the bit-identical result.  Two slots
+// by sequence parity: a rank can run at most one call ahead of its slowest peer.  The wait is bounded
+// (about 10 s of SM clocks); on expiry the error flag makes the host abort instead of hanging the GPU.
+__global__ void kern_p2p_allreduce(Mbox *mine, Mbox *const *peers, int rank, int world, unsigned long long seq,
+                                   int count, int isMax, double *values, Ctrl *ctrl)
+{
+    const int lane = threadIdx.x;
+    const int par = (int)(seq & 1ull);
+    if (lane < world)
+    {
+        Mbox *dst = peers[lane];
+        for (int k = 0; k < count; ++k) *((volatile double *)&dst->val[par][rank][k]) = values[k];
+        __threadfence_system();
+        *((volatile unsigned long long *)&dst->seq[par][rank]) = seq;
+        const long long t0 = clock64();
+        while (*((volatile unsigned long long *)&mine->seq[par][lane]) != seq)
+            if (clock64() - t0 > 20000000000ll) { mine->error = 1; break; }
+    }
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0)
+    {
+        for (int k = 0; k < count; ++k)
+        {
+            double acc = *((volatile double *)&mine->val[par][0][k]);
+            for (int r = 1; r < world; ++r)
+            {
+                const double x = *((volatile double *)&mine->val[par][r][k]);
+                acc = isMax ? ((acc < x) ? x : acc) : (acc + x);
+            }
+            values[k] = acc;
+        }
+        if (mine->error && ctrl) ctrl->status = SOLVE_DIVERGED;
+    }
+}
+
 // direct halo: store my boundary values into the neighbour's ghost entries (peer memory, NVLink)
 __global__ void __launch_bounds__(SF3D_BLOCK) kern_push(const double *__restrict__ x, const uint32_t *__restrict__ idx, uint32_t n,
                                                       double *__restrict__ peerX, const uint32_t *__restrict__ remoteIdx,
@@ -865,6 +908,14 @@ struct HaloPeer {
     // send entries lives in the neighbour's numbering (its ghost row)
     double *peerX[2]; uint32_t *remoteIdx;
 };
+// direct reductions: every rank owns a mailbox that all ranks can write through CUDA IPC
+#define SF3D_MAX_RANKS 16
+struct Mbox { double val[2][SF3D_MAX_RANKS][4]; unsigned long long seq[2][SF3D_MAX_RANKS]; int error; int pad; };
+static Mbox *g_mbox = nullptr;                       // this rank's mailbox (device memory)
+static Mbox *g_peerMbox[SF3D_MAX_RANKS] = {nullptr}; // host copy of the mapped pointers ([g_rank] = g_mbox)
+static Mbox **g_peerMboxDev = nullptr;               // the same table in device memory
+static unsigned long long g_seq = 0;
+static bool g_directReduce = false;
 static double *g_localX[2] = {nullptr, nullptr};     // this rank's x0 / x1 (exported to the neighbours)
 static bool g_directHalo = false;
 static std::vector<HaloPeer> g_halo;
@@ -924,6 +975,41 @@ void comm_clear_halo()
     }
     g_halo.clear();
     g_directHalo = false;
+    for (int r = 0; r < SF3D_MAX_RANKS; ++r)
+        if (g_peerMbox[r] && r != g_rank) { cudaIpcCloseMemHandle(g_peerMbox[r]); }
+    for (int r = 0; r < SF3D_MAX_RANKS; ++r) g_peerMbox[r] = nullptr;
+    dev_free(g_mbox); g_mbox = nullptr;
+    dev_free(g_peerMboxDev); g_peerMboxDev = nullptr;
+    g_directReduce = false; g_seq = 0;
+}
+// direct reductions: export this rank's mailbox / import the others'
+void comm_mailbox_export(unsigned char out[64])
+{
+    ensure_device();
+    if (g_world > SF3D_MAX_RANKS) throw DeviceError{-1, "too many ranks for the mailbox all-reduce", "comm_mailbox_export"};
+    if (!g_mbox) g_mbox = (Mbox *)dev_alloc(sizeof(Mbox));
+    cudaIpcMemHandle_t h;
+    CUDA_OK(cudaIpcGetMemHandle(&h, g_mbox));
+    memcpy(out, &h, 64);
+    g_peerMbox[g_rank] = g_mbox;
+}
+void comm_mailbox_import(int peer, const unsigned char handle[64])
+{
+    ensure_device();
+    if (peer < 0 || peer >= g_world || peer >= SF3D_MAX_RANKS || peer == g_rank) throw DeviceError{-1, "bad mailbox peer", "comm_mailbox_import"};
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void *p = nullptr;
+    CUDA_OK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    g_peerMbox[peer] = (Mbox *)p;
+    bool all = g_mbox != nullptr;
+    for (int r = 0; r < g_world; ++r) if (!g_peerMbox[r]) all = false;
+    if (all)
+    {
+        if (!g_peerMboxDev) g_peerMboxDev = (Mbox **)dev_alloc(SF3D_MAX_RANKS * sizeof(Mbox *));
+        h2d(g_peerMboxDev, g_peerMbox, SF3D_MAX_RANKS * sizeof(Mbox *));
+        g_directReduce = true;
+    }
 }
 // direct halo: export this rank's solution buffers / import a neighbour's
 void comm_ipc_export(double *x0, double *x1, unsigned char out[128])
@@ -977,9 +1063,16 @@ void comm_add_halo_peer(int peer, uint32_t nSend, const uint32_t *sendIdx, uint3
     if (nRecv) h2d(h.recvIdx, recvIdx, (size_t)nRecv * 4);
     g_halo.push_back(h);
 }
-void comm_allreduce(double *devValues, int count, bool isMax)
+void comm_allreduce(double *devValues, int count, bool isMax, Ctrl *ctrl)
 {
     if (g_world <= 1) return;
+    if (g_directReduce)
+    {
+        ++g_seq;
+        kern_p2p_allreduce<<<1, 32, 0, g_stream>>>(g_mbox, g_peerMboxDev, g_rank, g_world, g_seq, count, isMax ? 1 : 0, devValues, ctrl);
+        LAUNCH_CHECK();
+        return;
+    }
     NCCL_OK(nccl.AllReduce(devValues, devValues, (size_t)count, NCCL_FLOAT64, isMax ? NCCL_MAX : NCCL_SUM, g_comm, g_stream));
 }
 void comm_halo(double *x, const Ctrl *ctrl)
@@ -1067,7 +1160,7 @@ void k_assemble(const SF3DView &v, double dt, int approx, double dtMin)
     }
     if (v.world > 1)
     {
-        comm_allreduce(v.ctrl->red, 1, true);
+        comm_allreduce(v.ctrl->red, 1, true, v.ctrl);
         kern_rule_courant<<<1, 1, 0, g_stream>>>(v.ctrl, dt, dtMin); LAUNCH_CHECK();
     }
 }
@@ -1078,7 +1171,7 @@ void k_jacobi(const SF3DView &v, const double *xin, double *xout, int maxIter, d
     {
         ProfScope ps(SF3D_K_OTHER);
         comm_halo(xout, v.ctrl);                         // boundary rows of x -> neighbours' ghost rows
-        comm_allreduce(v.ctrl->red, 1, false);           // residual sum over ranks
+        comm_allreduce(v.ctrl->red, 1, false, v.ctrl);           // residual sum over ranks
         kern_rule_jacobi<<<1, 1, 0, g_stream>>>(v.ctrl, v.nGlobal, maxIter, tol); LAUNCH_CHECK();
     }
 }
@@ -1087,7 +1180,7 @@ void k_post(const SF3DView &v, const double *x, double dt, int mode)
     { ProfScope ps(SF3D_K_POST); kern_post<<<GRID(v.N)>>>(v, x, dt, mode); LAUNCH_CHECK(); }
     if (v.world > 1)
     {
-        comm_allreduce(v.ctrl->red, 2, false);
+        comm_allreduce(v.ctrl->red, 2, false, v.ctrl);
         kern_rule_post<<<1, 1, 0, g_stream>>>(v.ctrl); LAUNCH_CHECK();
     }
 }
@@ -1098,7 +1191,7 @@ void k_total_boundary_flow(const SF3DView &v, uint32_t bt)
     kern_total_boundary<<<GRID(v.N)>>>(v, bt); LAUNCH_CHECK();
     if (v.world > 1)
     {
-        comm_allreduce(v.ctrl->red, 1, false);
+        comm_allreduce(v.ctrl->red, 1, false, v.ctrl);
         kern_rule_boundary<<<1, 1, 0, g_stream>>>(v.ctrl); LAUNCH_CHECK();
     }
 }
@@ -1125,7 +1218,7 @@ void k_boundary_heat(const SF3DView &v, double maxTimeStep)
 {
     ProfScope ps(SF3D_K_OTHER);
     kern_boundary_heat<<<GRID(v.N)>>>(v, maxTimeStep); LAUNCH_CHECK();
-    if (v.world > 1) { comm_allreduce(v.ctrl->red, 1, true); kern_rule_heat_courant<<<1, 1, 0, g_stream>>>(v.ctrl); LAUNCH_CHECK(); }
+    if (v.world > 1) { comm_allreduce(v.ctrl->red, 1, true, v.ctrl); kern_rule_heat_courant<<<1, 1, 0, g_stream>>>(v.ctrl); LAUNCH_CHECK(); }
 }
 void k_heat_begin(const SF3DView &v, double dtHeat, double dtWater)
 {
@@ -1142,7 +1235,7 @@ void k_heat_jacobi(const SF3DView &v, const double *xin, double *xout, int maxIt
     if (v.world > 1)
     {
         comm_halo(xout, v.ctrl);
-        comm_allreduce(v.ctrl->red, 1, true);
+        comm_allreduce(v.ctrl->red, 1, true, v.ctrl);
         kern_rule_heat_jacobi<<<1, 1, 0, g_stream>>>(v.ctrl, maxIter, tol); LAUNCH_CHECK();
     }
 }
@@ -1150,7 +1243,7 @@ void k_heat_post(const SF3DView &v, const double *x, double dtHeat, double dtWat
 {
     ProfScope ps(SF3D_K_OTHER);
     kern_heat_post<<<GRID(v.N)>>>(v, x, dtHeat, dtWater, mode); LAUNCH_CHECK();
-    if (v.world > 1) { comm_allreduce(v.ctrl->red, 2, false); kern_rule_heat_post<<<1, 1, 0, g_stream>>>(v.ctrl); LAUNCH_CHECK(); }
+    if (v.world > 1) { comm_allreduce(v.ctrl->red, 2, false, v.ctrl); kern_rule_heat_post<<<1, 1, 0, g_stream>>>(v.ctrl); LAUNCH_CHECK(); }
 }
 void k_heat_accept(const SF3DView &v, double dtHeat, double dtWater)
 { ProfScope ps(SF3D_K_OTHER); kern_heat_accept<<<GRID(v.N)>>>(v, dtHeat, dtWater); LAUNCH_CHECK(); }

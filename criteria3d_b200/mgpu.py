@@ -41,12 +41,19 @@ def setup_slab(sf: SoilFluxes3D, rows: int, cols: int, n_soil_layers: int, rank:
 def wire_direct_halo(sf: SoilFluxes3D, slab: Slab, peers) -> None:
     """Exchange the CUDA IPC handles of every rank's solution buffers and tell the library where each
     send entry lives in the neighbour's numbering (= the neighbour's recv list towards this rank)."""
-    mine = torch.frombuffer(bytearray(sf.ipc_export()), dtype=torch.uint8).cuda()
+    reduce_direct = os.environ.get("SF3D_DIRECT_REDUCE", "1") != "0"
+    blob = sf.ipc_export() + (sf.mailbox_export() if reduce_direct else bytes(64))
+    mine = torch.frombuffer(bytearray(blob), dtype=torch.uint8).cuda()
     gathered = [torch.empty_like(mine) for _ in range(slab.world)]
     dist.all_gather(gathered, mine)
+    blobs = [bytes(g.cpu().numpy().tobytes()) for g in gathered]
     for p in peers:
         other = make_slab(slab.rows, slab.cols, slab.layers - 1, slab.world, p)
         o_peers, _o_send, o_recv = other.halo()
         remote = o_recv[o_peers.index(slab.rank)]
-        _ok(sf.ipc_import(p, bytes(gathered[p].cpu().numpy().tobytes()), remote), "sf3d_ext_ipc_import")
+        _ok(sf.ipc_import(p, blobs[p][:128], remote), "sf3d_ext_ipc_import")
+    if reduce_direct:
+        for p in range(slab.world):
+            if p != slab.rank:
+                _ok(sf.mailbox_import(p, blobs[p][128:192]), "sf3d_ext_mailbox_import")
     dist.barrier()

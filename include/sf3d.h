@@ -293,6 +293,12 @@ uint8_t sf3d_ext_set_halo(uint32_t n_peers, const int32_t *peers,
  * from a kernel that follows the sweep, instead of pack -> ncclSend/ncclRecv -> unpack. */
 uint8_t sf3d_ext_ipc_export(uint8_t handles[128]);
 uint8_t sf3d_ext_ipc_import(int peer, const uint8_t handles[128], uint32_t n, const uint32_t *remote_idx);
+/* product only, optional: direct reductions.  Every rank exports the CUDA IPC handle of a small mailbox
+ * and imports the mailboxes of ALL other ranks; the residual / Courant / balance all-reduces then run as
+ * one warp-sized kernel that stores into the peers' mailboxes over NVLink (deterministic rank-order fold)
+ * instead of ncclAllReduce. */
+uint8_t sf3d_ext_mailbox_export(uint8_t handle[64]);
+uint8_t sf3d_ext_mailbox_import(int peer, const uint8_t handle[64]);
 
 /* product only: the cudaStream_t every kernel of the library is launched on (for CUDA-event
  * timing from the harness); NULL in the CPU libraries. */

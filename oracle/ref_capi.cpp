@@ -268,6 +268,8 @@ uint8_t sf3d_ext_comm_unique_id(uint8_t id[128]) { (void)id; return SF3D_PARAMET
 uint8_t sf3d_ext_comm_init(int rank, int world, const uint8_t id[128]) { (void)rank; (void)world; (void)id; return SF3D_PARAMETER_ERROR; }
 uint8_t sf3d_ext_comm_finalize(void) { return SF3D_PARAMETER_ERROR; }
 uint8_t sf3d_ext_ipc_export(uint8_t h[128]) { (void)h; return SF3D_PARAMETER_ERROR; }
+uint8_t sf3d_ext_mailbox_export(uint8_t h[64]) { (void)h; return SF3D_PARAMETER_ERROR; }
+uint8_t sf3d_ext_mailbox_import(int p, const uint8_t h[64]) { (void)p; (void)h; return SF3D_PARAMETER_ERROR; }
 uint8_t sf3d_ext_ipc_import(int p, const uint8_t h[128], uint32_t n, const uint32_t *r) { (void)p; (void)h; (void)n; (void)r; return SF3D_PARAMETER_ERROR; }
 uint8_t sf3d_ext_set_halo(uint32_t n, const int32_t *p, const uint32_t *sc, const uint32_t *si, const uint32_t *rc, const uint32_t *ri, uint64_t ng)
 { (void)n; (void)p; (void)sc; (void)si; (void)rc; (void)ri; (void)ng; return SF3D_PARAMETER_ERROR; }
