@@ -424,6 +424,8 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_pack(const double *__restrict
 {
     for (uint32_t k = blockIdx.x * SF3D_BLOCK + threadIdx.x; k < n; k += gridDim.x * SF3D_BLOCK) buf[k] = x[idx[k]];
 }
+#define SF3D_MAX_RANKS 16
+struct Mbox { double val[2][SF3D_MAX_RANKS][4]; unsigned long long seq[2][SF3D_MAX_RANKS]; int error; int pad; };
 // All-reduce of up to four doubles over peer memory, one warp per rank: lane r stores this rank's values
 // and then the sequence number into rank r's mailbox (NVLink peer stores, system-scope fence in between),
 // then waits until rank r's contribution for the same sequence number has landed in the local mailbox;
@@ -909,8 +911,6 @@ struct HaloPeer {
     double *peerX[2]; uint32_t *remoteIdx;
 };
 // direct reductions: every rank owns a mailbox that all ranks can write through CUDA IPC
-#define SF3D_MAX_RANKS 16
-struct Mbox { double val[2][SF3D_MAX_RANKS][4]; unsigned long long seq[2][SF3D_MAX_RANKS]; int error; int pad; };
 static Mbox *g_mbox = nullptr;                       // this rank's mailbox (device memory)
 static Mbox *g_peerMbox[SF3D_MAX_RANKS] = {nullptr}; // host copy of the mapped pointers ([g_rank] = g_mbox)
 static Mbox **g_peerMboxDev = nullptr;               // the same table in device memory
