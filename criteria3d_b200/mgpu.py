@@ -33,7 +33,17 @@ def setup_slab(sf: SoilFluxes3D, rows: int, cols: int, n_soil_layers: int, rank:
         peers, send, recv = slab.halo()
         _ok(sf.set_halo(peers, send, recv, slab.n_global), "sf3d_ext_set_halo")
         if os.environ.get("SF3D_DIRECT_HALO", "1") != "0":
-            wire_direct_halo(sf, slab, peers)
+            ok = 1
+            try:
+                wire_direct_halo(sf, slab, peers)
+            except Exception as e:  # noqa: BLE001  (e.g. no peer access between two devices)
+                print(f"[sf3d] rank {rank}: direct peer-memory wiring failed ({e}); falling back to NCCL", flush=True)
+                ok = 0
+            # the ranks must agree: one failure puts everybody back on the NCCL halo / all-reduce
+            flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                _ok(sf.set_halo(peers, send, recv, slab.n_global), "sf3d_ext_set_halo")      # drops every IPC mapping
         _ok(sf.initializeBalance(), "initializeBalance")
     return slab, cat
 
@@ -56,4 +66,3 @@ def wire_direct_halo(sf: SoilFluxes3D, slab: Slab, peers) -> None:
         for p in range(slab.world):
             if p != slab.rank:
                 _ok(sf.mailbox_import(p, blobs[p][128:192]), "sf3d_ext_mailbox_import")
-    dist.barrier()
