@@ -132,6 +132,15 @@ def prescribed_and_urban(sf, threads=1):
     return snapshot(sf, cat.n_nodes, dts)
 
 
+def dry_no_forcing(sf, threads=1):
+    """empty forcing: no rain, no sinks; redistribution and free drainage only, the time step grows to its
+    maximum (doubling rule, water.cpp:197-200) and whole-hour steps are accepted"""
+    cat = Catchment(12, 10, 4)
+    setup(sf, cat, threads=threads)
+    dts = run_hours(sf, cat, [0.0, 0.0, 0.0])
+    return snapshot(sf, cat.n_nodes, dts)
+
+
 def saturated_bottom(sf, threads=1):
     """C4-like: lower third of the layers start saturated (psi = +0.1 m)"""
     return storm(sf, shape=(20, 20, 9), hours=(10.0,), threads=threads, saturated_bottom=True)
@@ -257,6 +266,7 @@ SCENARIOS = {
     "evaporation_after_rain": evaporation_after_rain,
     "prescribed_and_urban": prescribed_and_urban,
     "saturated_bottom": saturated_bottom,
+    "dry_no_forcing": dry_no_forcing,
     "ragged_raster": ragged_raster,
     "config1_bundled_catchment": config1_bundled_catchment,
     "scalar_api_column": scalar_api_column,
