@@ -96,3 +96,82 @@ def make_slab(rows: int, cols: int, n_soil_layers: int, world: int, rank: int) -
 def slab_catchment(slab: Slab, **kw) -> Catchment:
     """The local raster of a slab: the same seeded generator evaluated on the slab's global rows."""
     return Catchment(slab.local_rows, slab.cols, slab.layers - 1, row0=slab.local_row0, global_rows=slab.rows, **kw)
+
+
+# ---------------------------------------------------------------------------------------------
+# generic node/link graphs (not rasters): partition by y quantiles, ghost set = link closure
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class RankGraph:
+    rank: int
+    owned: np.ndarray            # global ids owned by this rank
+    ghosts: np.ndarray           # global ids of the halo copies this rank needs
+    local_to_global: np.ndarray  # local numbering: owned surface, ghost surface, owned soil, ghost soil
+    n_surface_local: int
+    peers: list                  # neighbouring ranks
+    send: list                   # per peer: LOCAL ids of owned nodes the peer needs (ascending global id)
+    recv: list                   # per peer: LOCAL ids of the ghosts owned by that peer (ascending global id)
+
+    def global_to_local(self) -> dict:
+        return {int(g): k for k, g in enumerate(self.local_to_global)}
+
+
+def partition_graph(y: np.ndarray, surface_flag: np.ndarray, link_type: np.ndarray, link_index: np.ndarray,
+                    world: int) -> list[RankGraph]:
+    """Partition an arbitrary soilFluxes3D graph over `world` ranks (non-grid case).
+
+    link_type / link_index: (10, N) slot tables as the API stores them (slot 0 Up, 1 Down, 2.. Lateral).
+    Vertical links never cross ranks: nodes are grouped into columns by following Up links, columns are
+    sorted by the y of their top node (north to south, ties by id) and cut into `world` contiguous groups
+    of near-equal node count.  Ghosts of a rank = link targets of its owned nodes that another rank owns.
+    """
+    n = y.shape[0]
+    up_t, up_i = link_type[0], link_index[0]
+    root = np.arange(n, dtype=np.int64)
+    for i in range(n):                       # Up neighbours are created before their lower nodes in every caller
+        if up_t[i] != 0:
+            j = int(up_i[i])
+            root[i] = root[j] if j < i else j
+    for _ in range(64):                      # path compression for graphs numbered differently
+        nxt = root[root]
+        if np.array_equal(nxt, root):
+            break
+        root = nxt
+    cols, inv, counts = np.unique(root, return_inverse=True, return_counts=True)
+    order = np.lexsort((cols, -y[cols]))     # north (large y) first, ties by id
+    cum = np.cumsum(counts[order])
+    owner_of_col = np.empty(len(cols), np.int64)
+    owner_of_col[order] = np.minimum((cum - 1) * world // cum[-1], world - 1)
+    owner = owner_of_col[inv]
+
+    out = []
+    surface_flag = surface_flag.astype(bool)
+    for r in range(world):
+        owned = np.flatnonzero(owner == r)
+        tgt = []
+        for s in range(link_type.shape[0]):
+            has = link_type[s, owned] != 0
+            tgt.append(link_index[s, owned][has].astype(np.int64))
+        tgt = np.unique(np.concatenate(tgt)) if tgt else np.zeros(0, np.int64)
+        ghosts = tgt[owner[tgt] != r]
+        l2g = np.concatenate([owned[surface_flag[owned]], ghosts[surface_flag[ghosts]],
+                              owned[~surface_flag[owned]], ghosts[~surface_flag[ghosts]]])
+        out.append(RankGraph(rank=r, owned=owned, ghosts=ghosts, local_to_global=l2g,
+                             n_surface_local=int(surface_flag[owned].sum() + surface_flag[ghosts].sum()),
+                             peers=[], send=[], recv=[]))
+    for r, g in enumerate(out):
+        g2l = g.global_to_local()
+        for p in sorted(set(owner[g.ghosts].tolist())):
+            mine_needed_by_p = np.intersect1d(out[p].ghosts, g.owned)          # ascending global id on both sides
+            from_p = g.ghosts[owner[g.ghosts] == p]
+            g.peers.append(int(p))
+            g.recv.append(np.array([g2l[int(x)] for x in np.sort(from_p)], np.uint32))
+            g.send.append(np.array([g2l[int(x)] for x in mine_needed_by_p], np.uint32))
+        for p in range(world):                                                  # peers that only receive from me
+            if p != r and p not in g.peers:
+                need = np.intersect1d(out[p].ghosts, g.owned)
+                if need.size:
+                    g.peers.append(int(p))
+                    g.send.append(np.array([g2l[int(x)] for x in need], np.uint32))
+                    g.recv.append(np.zeros(0, np.uint32))
+    return out

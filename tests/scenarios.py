@@ -141,6 +141,23 @@ def dry_no_forcing(sf, threads=1):
     return snapshot(sf, cat.n_nodes, dts)
 
 
+def culvert_outlet(sf, threads=1):
+    """Culvert boundary on part of the outlet row.  Unreachable in the reference (setCulvert writes through
+    a pointer array that is never allocated, soilFluxes3D.cpp:146,586: SURVEY Q5), so this case pins the
+    product against the C restatement of water.cpp:749-795 (mean-head form of v1) only."""
+    cat = Catchment(14, 12, 3)
+    setup(sf, cat, threads=threads)
+    last_row = (cat.rows - 1) * cat.cols
+    for c in range(3, 9):
+        _ok(sf.setCulvert(last_row + c, 0.015, 0.02, 0.8, 0.5), "setCulvert")
+    assert sf.setCulvert(cat.n_surface + 1, 0.015, 0.02, 0.8, 0.5) == 1          # soil node -> IndexError
+    _ok(sf.initializeBalance(), "balance")
+    dts = run_hours(sf, cat, [60.0], max_steps=60)
+    out = snapshot(sf, cat.n_nodes, dts)
+    out["culvert_total"] = np.float64(sf.getTotalBoundaryWaterFlow(int(BoundaryType.Culvert)))
+    return out
+
+
 def saturated_bottom(sf, threads=1):
     """C4-like: lower third of the layers start saturated (psi = +0.1 m)"""
     return storm(sf, shape=(20, 20, 9), hours=(10.0,), threads=threads, saturated_bottom=True)

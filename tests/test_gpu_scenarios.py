@@ -21,3 +21,18 @@ def test_heat_scenario(product, checker, name):
     a = HEAT_SCENARIOS[name](product)
     b = HEAT_SCENARIOS[name](checker)
     compare(a, b, exact=False)
+
+
+def test_culvert_against_restatement(product):
+    """culvert boundary: product vs the C restatement (the reference cannot run it)"""
+    import numpy as np
+    from criteria3d_b200 import ORACLE_LIB, SoilFluxes3D
+    from scenarios import culvert_outlet
+    if not ORACLE_LIB.exists():
+        pytest.skip("oracle library not built")
+    a = culvert_outlet(product)
+    b = culvert_outlet(SoilFluxes3D(ORACLE_LIB))
+    assert b["culvert_total"] < 0.0                      # water does leave through the culvert
+    assert abs(a["culvert_total"] - b["culvert_total"]) <= 1e-6 * abs(b["culvert_total"])
+    a.pop("culvert_total"); b.pop("culvert_total")
+    compare(a, b, exact=False)

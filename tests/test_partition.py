@@ -112,3 +112,58 @@ def test_halo_exchange_over_gloo(world):
         p.join(timeout=60)
     assert all(ok for _, ok, _, _ in res), res
     assert all(n == ng for _, _, n, ng in res), res
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_generic_graph_partition_closure_and_halo(world):
+    """Non-grid path: partition a node/link graph by y quantiles; one 'Jacobi-like' neighbour sum computed
+    on the local graphs after a halo exchange along the send/recv lists equals the global one."""
+    if not ORACLE_LIB.exists():
+        pytest.skip("oracle library not built")
+    from criteria3d_b200.partition import partition_graph
+    sf = SoilFluxes3D(ORACLE_LIB)
+    valid = np.ones((9, 7), bool)
+    valid[0:2, 0:3] = False
+    valid[5, 4] = False
+    cat = Catchment(9, 7, 3, valid=valid)
+    setup(sf, cat, threads=1)
+    n = cat.n_nodes
+    lt = np.stack([sf.link_table(s, 0, n)[0] for s in range(10)])
+    li = np.stack([sf.link_table(s, 0, n)[1] for s in range(10)])
+    surf = sf.node_meta(0, n)[0]
+    H = sf.get_field(4, 0, n)
+    psi = sf.get_field(3, 0, n)
+    yy = np.repeat(np.arange(9)[::-1], 7).reshape(9, 7)[valid].astype(float)      # y of each cell, north = large
+    y = np.tile(yy, cat.layers)
+    parts = partition_graph(y, surf, lt, li, world)
+    assert sorted(np.concatenate([p.owned for p in parts]).tolist()) == list(range(n))
+    xg = np.sin(np.arange(n) * 0.61) + (H - psi)
+    want = np.zeros(n)
+    for s in range(10):
+        has = lt[s] != 0
+        want[has] += xg[li[s][has]]
+    # local vectors: owned values known, ghosts filled through the halo lists
+    loc = []
+    for p in parts:
+        x = np.full(len(p.local_to_global), np.nan)
+        g2l = p.global_to_local()
+        for g in p.owned:
+            x[g2l[int(g)]] = xg[g]
+        assert p.n_surface_local == int(surf[p.local_to_global].sum())
+        assert np.all(surf[p.local_to_global[: p.n_surface_local]] == 1)            # surface nodes first
+        loc.append(x)
+    for p in parts:
+        for peer, s_idx in zip(p.peers, p.send):
+            q = parts[peer]
+            r_idx = q.recv[q.peers.index(p.rank)]
+            assert len(r_idx) == len(s_idx)
+            loc[peer][r_idx] = loc[p.rank][s_idx]
+    for p in parts:
+        g2l = p.global_to_local()
+        assert not np.isnan(loc[p.rank]).any()
+        for g in p.owned:
+            acc = 0.0
+            for s in range(10):
+                if lt[s][g] != 0:
+                    acc += loc[p.rank][g2l[int(li[s][g])]]
+            assert acc == pytest.approx(want[g], rel=1e-14, abs=1e-12)
