@@ -154,11 +154,12 @@ class Counters(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
-KERNEL_NAMES = ["begin_try", "node_phase", "assemble", "jacobi", "post", "accept", "other"]
+KERNEL_NAMES = ["begin_try", "node_phase", "assemble", "jacobi", "post", "accept", "other", "heat_coeffs",
+                "heat_flux_snapshot", "heat_boundary", "heat_assemble", "heat_jacobi", "heat_post", "heat_accept", "comm"]
 
 
 class KernelTimes(C.Structure):
-    _fields_ = [("ms", C.c_double * 7), ("launches", C.c_uint64 * 7)]
+    _fields_ = [("ms", C.c_double * 15), ("launches", C.c_uint64 * 15)]
 
 
 u8, u16, u32, dbl, cint = C.c_uint8, C.c_uint16, C.c_uint32, C.c_double, C.c_int

@@ -48,7 +48,9 @@ bool comm_direct_halo();
 
 // ---- kernels -----------------------------------------------------------------------------
 int  reduce_blocks(uint32_t n);          // grid size used by all reducing kernels for n rows
+int  wide_blocks(uint32_t n);            // grid size of the node-phase / assembly kernels
 void k_link_geometry(const SF3DView &v, int *surfaceOrderOk);
+void k_heat_geometry(const SF3DView &v);       // static per-node pressure and per-link 3-D distance
 bool k_build_patterns(const SF3DView &v, uint16_t *pid, int32_t *table, uint32_t *hotPid, int32_t hotOff[SF3D_NLINK]);   // pattern-compressed column indices
 size_t pattern_table_bytes();
 void k_begin_try(const SF3DView &v);

@@ -70,7 +70,8 @@ struct State {
                    hbSens, hbLat, hbRad, hbAdv, hbFixT, hbFixDepth;
     Mirror<double> lfluxes;               // [type][slot][node]; 1 type (HeatTotal) unless save mode All (9)
     int hfTypesAllocated = 0;
-    double *hFlux = nullptr, *lwFlux = nullptr, *lvFlux = nullptr, *hdiag = nullptr, *hTVK = nullptr, *hIVK = nullptr, *hCond = nullptr;
+    double *hFlux = nullptr, *lwFlux = nullptr, *lvFlux = nullptr, *hdiag = nullptr, *hTVK = nullptr, *hIVK = nullptr, *hCond = nullptr,
+           *hTm = nullptr, *hTLK = nullptr, *hTLKh = nullptr, *hPress = nullptr, *ldist3 = nullptr;
     // device-only
     double *bestH = nullptr, *SeOld = nullptr, *wFlow = nullptr, *lgeom = nullptr, *mval = nullptr,
            *b = nullptr, *cap = nullptr, *x0 = nullptr, *x1 = nullptr, *partA = nullptr, *partB = nullptr,
@@ -134,6 +135,7 @@ void fill_view()
         v.hbFixT = S.hbFixT.d; v.hbFixDepth = S.hbFixDepth.d;
         v.lwFlux = S.lwFlux; v.lvFlux = S.lvFlux; v.lfluxes = S.lfluxes.d; v.hdiag = S.hdiag;
         v.hTVK = S.hTVK; v.hIVK = S.hIVK; v.hCond = S.hCond;
+        v.hTm = S.hTm; v.hTLK = S.hTLK; v.hTLKh = S.hTLKh; v.hPress = S.hPress; v.ldist3 = S.ldist3;
     }
 }
 
@@ -193,6 +195,7 @@ uint8_t sync_to_device(bool finalizeTopology = true)
         S.patternsOk = false;
         fill_view();
         k_link_geometry(S.eng.v, &ok);
+        if (S.heat) k_heat_geometry(S.eng.v);
         S.patternsOk = k_build_patterns(S.eng.v, S.pid, S.pattern, &S.hotPid, S.hotOff) && getenv("SF3D_EXPLICIT_INDEX") == nullptr;
         fill_view();
         S.topoDirty = false;
@@ -263,7 +266,7 @@ void release_all()
     S.T.release(); S.oldT.release(); S.hSink.release(); S.lfluxes.release();
     collect_heat_mirrors();
     for (Mirror<double> *m : heat_boundary_mirrors) m->release();
-    { double **hd[] = {&S.hFlux, &S.lwFlux, &S.lvFlux, &S.hdiag, &S.hTVK, &S.hIVK, &S.hCond}; for (double **p : hd) { dev_free(*p); *p = nullptr; } }
+    { double **hd[] = {&S.hFlux, &S.lwFlux, &S.lvFlux, &S.hdiag, &S.hTVK, &S.hIVK, &S.hCond, &S.hTm, &S.hTLK, &S.hTLKh, &S.hPress, &S.ldist3}; for (double **p : hd) { dev_free(*p); *p = nullptr; } }
     S.hfTypesAllocated = 0;
     double **devOnly[] = {&S.bestH, &S.SeOld, &S.wFlow, &S.lgeom, &S.mval, &S.b, &S.cap, &S.x0, &S.x1,
                           &S.partA, &S.partB, &S.partC, &S.scratch};
@@ -309,7 +312,7 @@ uint8_t sf3d_initialize(uint32_t nrNodes, uint32_t nrSurfaceNodes, uint8_t nrLat
         S.pid = (uint16_t *)dev_alloc(N * 2); S.pattern = (int32_t *)dev_alloc(pattern_table_bytes());
         S.b = (double *)dev_alloc(N * 8); S.cap = (double *)dev_alloc(N * 8);
         S.x0 = (double *)dev_alloc(N * 8); S.x1 = (double *)dev_alloc(N * 8);
-        const size_t nb = (size_t)reduce_blocks(0xFFFFFFFFu);
+        const size_t nb = (size_t)std::max(reduce_blocks(0xFFFFFFFFu), wide_blocks(0xFFFFFFFFu));
         S.partA = (double *)dev_alloc(nb * 8); S.partB = (double *)dev_alloc(nb * 8); S.partC = (double *)dev_alloc(nb * 8);
         S.ctrl = (Ctrl *)dev_alloc(sizeof(Ctrl));
         if (S.heat)
@@ -319,6 +322,8 @@ uint8_t sf3d_initialize(uint32_t nrNodes, uint32_t nrSurfaceNodes, uint8_t nrLat
             for (Mirror<double> *m : heat_boundary_mirrors) m->alloc(N);
             S.hFlux = (double *)dev_alloc(N * 8); S.hdiag = (double *)dev_alloc(N * 8);
             S.hTVK = (double *)dev_alloc(N * 8); S.hIVK = (double *)dev_alloc(N * 8); S.hCond = (double *)dev_alloc(N * 8);
+            S.hTm = (double *)dev_alloc(N * 8); S.hTLK = (double *)dev_alloc(N * 8); S.hTLKh = (double *)dev_alloc(N * 8);
+            S.hPress = (double *)dev_alloc(N * 8); S.ldist3 = (double *)dev_alloc(L * 8);
             S.lwFlux = (double *)dev_alloc(L * 8); S.lvFlux = (double *)dev_alloc(L * 8);
             S.hfTypesAllocated = (S.hfMode == 2) ? 9 : 1;
             S.lfluxes.alloc((size_t)S.hfTypesAllocated * L);
@@ -407,6 +412,7 @@ uint8_t sf3d_set_soil_properties(uint16_t nrSoil, uint8_t nrHorizon, double VG_a
     r.organicMatter = organicMatter; r.clay = clay;
     r.invM = 1.0 / r.m;
     r.invSc = 1.0 / r.Sc;
+    r.etaClay = 1. + 2.6 / sqrt(r.clay);
     r.ScPowInvM = pow(r.Sc, r.invM);
     r.tDen = 1.0 - pow(1.0 - r.ScPowInvM, r.m);
 
@@ -784,6 +790,7 @@ static SF3DView host_view()
     v.soil = S.soils.data();
     v.wrcModel = g_params.wrcModel;
     v.computeHeatVapor = S.heatVapor;
+    v.hPress = nullptr; v.ldist3 = nullptr; v.hTm = v.hTLK = v.hTLKh = nullptr;      // device-only tables
     return v;
 }
 uint8_t sf3d_set_node_heat_sink_source(uint32_t i, double q)
@@ -1146,7 +1153,7 @@ uint8_t sf3d_ext_jacobi_sweep(uint32_t n, uint32_t nSurface, const uint8_t *ncol
         double *dmv = (double *)dev_alloc(mv.size() * 8); uint32_t *dmc = (uint32_t *)dev_alloc(mc.size() * 4);
         double *db = (double *)dev_alloc((size_t)n * 8), *dz = (double *)dev_alloc((size_t)n * 8);
         double *dx0 = (double *)dev_alloc((size_t)n * 8), *dx1 = (double *)dev_alloc((size_t)n * 8);
-        const size_t nb = (size_t)reduce_blocks(0xFFFFFFFFu);
+        const size_t nb = (size_t)std::max(reduce_blocks(0xFFFFFFFFu), wide_blocks(0xFFFFFFFFu));
         double *part = (double *)dev_alloc(nb * 8);
         Ctrl *ctrl = (Ctrl *)dev_alloc(sizeof(Ctrl));
         h2d(dmv, mv.data(), mv.size() * 8); h2d(dmc, mc.data(), mc.size() * 4);

@@ -27,6 +27,10 @@ namespace sf3d {
 
 #define SF3D_BLOCK 256
 #define SF3D_MAX_BLOCKS (148 * 8)
+#ifndef SF3D_WIDE_BLOCKS
+#define SF3D_WIDE_BLOCKS (148 * 48)         // grid cap of the fp64-heavy node / assembly kernels (a multiple of every
+                                            // residency below, short tail wave)
+#endif
 
 static cudaStream_t g_stream = nullptr;
 static int g_device = -1;
@@ -136,6 +140,13 @@ void dev_sync() { ensure_device(); CUDA_OK(cudaStreamSynchronize(g_stream)); }
 uint64_t launches() { return g_launches; }
 void *dev_stream() { ensure_device(); return (void *)g_stream; }
 
+int wide_blocks(uint32_t n)
+{
+    long b = ((long)n + SF3D_BLOCK - 1) / SF3D_BLOCK;
+    if (b < 1) b = 1;
+    if (b > SF3D_WIDE_BLOCKS) b = SF3D_WIDE_BLOCKS;
+    return (int)b;
+}
 int reduce_blocks(uint32_t n)
 {
     long b = ((long)n + SF3D_BLOCK - 1) / SF3D_BLOCK;
@@ -230,6 +241,13 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_link_geometry(SF3DView v, int
     }
 }
 
+// static heat geometry: atmospheric pressure at the node's altitude and the 3-D distance of every link
+__global__ void __launch_bounds__(SF3D_BLOCK) kern_heat_geometry(SF3DView v)
+{
+    for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
+        sf3d_row_heat_geometry(v, i);
+}
+
 // ---- pattern compression of the column indices ------------------------------------------------
 // For every node the ten column offsets (mcol[c][i] - i) form a "link pattern"; a DEM catchment has a
 // few dozen distinct ones (interior, edges, corners x top/middle/bottom layer; more for ragged
@@ -322,8 +340,11 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_restore_old(SF3DView v)
         sf3d_row_restore_old(v, i);
 }
 
+#ifndef SF3D_NODE_BLOCKS
+#define SF3D_NODE_BLOCKS 8
+#endif
 template <bool HEAT>
-__global__ void __launch_bounds__(SF3D_BLOCK) kern_node_phase(SF3DView v, double dt, int withCapacity)
+__global__ void __launch_bounds__(SF3D_BLOCK, SF3D_NODE_BLOCKS) kern_node_phase(SF3DView v, double dt, int withCapacity)
 {
     for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
         sf3d_row_node_phase<HEAT>(v, i, dt, withCapacity);
@@ -365,8 +386,18 @@ __global__ void kern_rule_boundary(Ctrl *c) { c->boundarySum = c->red[0]; }
 // link phase: conductances, diagonal, row normalisation, right-hand side, per-row Courant;
 // the last block publishes max Courant and arms the on-device solver state
 // (CPUSolver::checkCourant test, cpusolver.cpp:248-260).  Ghost rows are not assembled.
+// Resident blocks per SM requested from ptxas.  These kernels are chains of dependent fp64 operations
+// (pow / log / divisions) behind scattered gathers: measured on B200 they run 1.5-2x faster with 40 / 32
+// registers and 1536 / 2048 resident threads per SM (a few spilled words) than unconstrained at 64 / 54
+// registers (profiles/r01_occupancy_ab.json).
+#ifndef SF3D_HEAT_ASSEMBLE_BLOCKS
+#define SF3D_HEAT_ASSEMBLE_BLOCKS 4
+#endif
+#ifndef SF3D_ASSEMBLE_BLOCKS
+#define SF3D_ASSEMBLE_BLOCKS 6
+#endif
 template <bool HEAT>
-__global__ void __launch_bounds__(SF3D_BLOCK) kern_assemble(SF3DView v, double dt, int approx, double dtMin)
+__global__ void __launch_bounds__(SF3D_BLOCK, HEAT ? SF3D_HEAT_ASSEMBLE_BLOCKS : SF3D_ASSEMBLE_BLOCKS) kern_assemble(SF3DView v, double dt, int approx, double dtMin)
 {
     __shared__ double sh[SF3D_BLOCK / 32];
     __shared__ double ksh[SF3D_NLINK * SF3D_BLOCK];          // ten conductances per thread, conflict-free layout
@@ -1104,10 +1135,15 @@ void comm_halo(double *x, const Ctrl *ctrl)
 // launchers
 // ------------------------------------------------------------------------------------------
 #define GRID(n) reduce_blocks(n), SF3D_BLOCK, 0, g_stream
+#define WIDE_GRID(n) wide_blocks(n), SF3D_BLOCK, 0, g_stream
 
 void dev_fill_f64(double *p, size_t n, double value)
 { ensure_device(); kern_fill<<<reduce_blocks((uint32_t)(n > 0xFFFFFFFFull ? 0xFFFFFFFFull : n)), 256, 0, g_stream>>>(p, n, value); LAUNCH_CHECK(); }
 
+void k_heat_geometry(const SF3DView &v)
+{
+    kern_heat_geometry<<<GRID(v.N)>>>(v); LAUNCH_CHECK();
+}
 void k_link_geometry(const SF3DView &v, int *surfaceOrderOk)
 {
     int *flag = (int *)dev_alloc(sizeof(int));
@@ -1146,16 +1182,16 @@ void k_restore_old(const SF3DView &v) { ProfScope ps(SF3D_K_OTHER); kern_restore
 void k_node_phase(const SF3DView &v, double dt, int withCapacity)
 {
     ProfScope ps(SF3D_K_NODE_PHASE);
-    if (v.computeHeat) kern_node_phase<true><<<GRID(v.N)>>>(v, dt, withCapacity);
-    else kern_node_phase<false><<<GRID(v.N)>>>(v, dt, withCapacity);
+    if (v.computeHeat) kern_node_phase<true><<<WIDE_GRID(v.N)>>>(v, dt, withCapacity);
+    else kern_node_phase<false><<<WIDE_GRID(v.N)>>>(v, dt, withCapacity);
     LAUNCH_CHECK();
 }
 void k_assemble(const SF3DView &v, double dt, int approx, double dtMin)
 {
     {
         ProfScope ps(SF3D_K_ASSEMBLE);
-        if (v.computeHeat) kern_assemble<true><<<GRID(v.N)>>>(v, dt, approx, dtMin);
-        else kern_assemble<false><<<GRID(v.N)>>>(v, dt, approx, dtMin);
+        if (v.computeHeat) kern_assemble<true><<<WIDE_GRID(v.N)>>>(v, dt, approx, dtMin);
+        else kern_assemble<false><<<WIDE_GRID(v.N)>>>(v, dt, approx, dtMin);
         LAUNCH_CHECK();
     }
     if (v.world > 1)
@@ -1169,7 +1205,7 @@ void k_jacobi(const SF3DView &v, const double *xin, double *xout, int maxIter, d
     { ProfScope ps(SF3D_K_JACOBI); kern_jacobi<<<GRID(v.N)>>>(v, xin, xout, maxIter, tol); LAUNCH_CHECK(); }
     if (v.world > 1)
     {
-        ProfScope ps(SF3D_K_OTHER);
+        ProfScope ps(SF3D_K_COMM);
         comm_halo(xout, v.ctrl);                         // boundary rows of x -> neighbours' ghost rows
         comm_allreduce(v.ctrl->red, 1, false, v.ctrl);           // residual sum over ranks
         kern_rule_jacobi<<<1, 1, 0, g_stream>>>(v.ctrl, v.nGlobal, maxIter, tol); LAUNCH_CHECK();
@@ -1209,28 +1245,28 @@ void k_build_grid(const SF3DView &v, const GridDev &g)
 void k_update_conductance(const SF3DView &v) { ProfScope ps(SF3D_K_OTHER); kern_update_conductance<<<GRID(v.N)>>>(v); LAUNCH_CHECK(); }
 void k_save_water_fluxes(const SF3DView &v, double dtHeat, double dtWater)
 {
-    ProfScope ps(SF3D_K_OTHER);
-    kern_heat_coeffs<<<GRID(v.N)>>>(v, dtHeat, dtWater); LAUNCH_CHECK();
+    { ProfScope ps(SF3D_K_HEAT_COEFFS); kern_heat_coeffs<<<GRID(v.N)>>>(v, dtHeat, dtWater); LAUNCH_CHECK(); }
+    ProfScope ps(SF3D_K_HEAT_FLUX_SNAPSHOT);
     kern_save_water_fluxes<<<GRID(v.N)>>>(v, dtHeat, dtWater); LAUNCH_CHECK();
 }
 void k_reset_water_fluxes(const SF3DView &v) { if (v.hfSaveMode == 2) { kern_reset_water_fluxes<<<GRID(v.N)>>>(v); LAUNCH_CHECK(); } }
 void k_boundary_heat(const SF3DView &v, double maxTimeStep)
 {
-    ProfScope ps(SF3D_K_OTHER);
+    ProfScope ps(SF3D_K_HEAT_BOUNDARY);
     kern_boundary_heat<<<GRID(v.N)>>>(v, maxTimeStep); LAUNCH_CHECK();
     if (v.world > 1) { comm_allreduce(v.ctrl->red, 1, true, v.ctrl); kern_rule_heat_courant<<<1, 1, 0, g_stream>>>(v.ctrl); LAUNCH_CHECK(); }
 }
 void k_heat_begin(const SF3DView &v, double dtHeat, double dtWater)
 {
-    ProfScope ps(SF3D_K_OTHER);
+    ProfScope ps(SF3D_K_HEAT_COEFFS);
     kern_heat_begin<<<GRID(v.N)>>>(v, dtHeat, dtWater); LAUNCH_CHECK();
     kern_heat_coeffs<<<GRID(v.N)>>>(v, dtHeat, dtWater); LAUNCH_CHECK();
 }
 void k_heat_assemble(const SF3DView &v, double dtHeat, double dtWater)
-{ ProfScope ps(SF3D_K_OTHER); kern_heat_assemble<<<GRID(v.N)>>>(v, dtHeat, dtWater); LAUNCH_CHECK(); }
+{ ProfScope ps(SF3D_K_HEAT_ASSEMBLE); kern_heat_assemble<<<GRID(v.N)>>>(v, dtHeat, dtWater); LAUNCH_CHECK(); }
 void k_heat_jacobi(const SF3DView &v, const double *xin, double *xout, int maxIter, double tol)
 {
-    ProfScope ps(SF3D_K_OTHER);
+    ProfScope ps(SF3D_K_HEAT_JACOBI);
     kern_heat_jacobi<<<GRID(v.N)>>>(v, xin, xout, maxIter, tol); LAUNCH_CHECK();
     if (v.world > 1)
     {
@@ -1241,12 +1277,12 @@ void k_heat_jacobi(const SF3DView &v, const double *xin, double *xout, int maxIt
 }
 void k_heat_post(const SF3DView &v, const double *x, double dtHeat, double dtWater, int mode)
 {
-    ProfScope ps(SF3D_K_OTHER);
+    ProfScope ps(SF3D_K_HEAT_POST);
     kern_heat_post<<<GRID(v.N)>>>(v, x, dtHeat, dtWater, mode); LAUNCH_CHECK();
     if (v.world > 1) { comm_allreduce(v.ctrl->red, 2, false, v.ctrl); kern_rule_heat_post<<<1, 1, 0, g_stream>>>(v.ctrl); LAUNCH_CHECK(); }
 }
 void k_heat_accept(const SF3DView &v, double dtHeat, double dtWater)
-{ ProfScope ps(SF3D_K_OTHER); kern_heat_accept<<<GRID(v.N)>>>(v, dtHeat, dtWater); LAUNCH_CHECK(); }
+{ ProfScope ps(SF3D_K_HEAT_ACCEPT); kern_heat_accept<<<GRID(v.N)>>>(v, dtHeat, dtWater); LAUNCH_CHECK(); }
 void k_heat_copy_T(const SF3DView &v, int mode) { kern_heat_copy_T<<<GRID(v.N)>>>(v, mode); LAUNCH_CHECK(); }
 void k_halo(double *x) { comm_halo(x, nullptr); }
 

@@ -146,9 +146,8 @@ SF3D_HD void sf3d_row_restore_old(const SF3DView &v, uint32_t i) { v.H[i] = v.ol
 //   Water::computeCapacity (water.cpp:279-297) + Water::updateBoundaryWaterData (water.cpp:632-807)
 // Heat hooks (vapour conductivity, HeatSurface evaporation) live in sf3d_rows_heat.h.
 // ==========================================================================================
-SF3D_HD double sf3d_heat_vapor_K(const SF3DView &v, uint32_t i);                       // soilPhysics.cpp:168-169
-SF3D_HD double sf3d_heat_water_tvk(const SF3DView &v, uint32_t i);
-SF3D_HD double sf3d_heat_dthetav_dh(const SF3DView &v, uint32_t i, double dThetadH);     // soilPhysics.cpp:287-299
+SF3D_HD double sf3d_heat_node_water(const SF3DView &v, uint32_t i, const SoilRec &s, double H, double z, double Se, double K,
+                                   const double *dThetadH, double *dThetaVdH);
 SF3D_HD double sf3d_heat_surface_boundary(const SF3DView &v, uint32_t i, double dt, double *upExtra);
 SF3D_HD double sf3d_heat_surface_pull(const SF3DView &v, uint32_t i, double dt, int *active);
 
@@ -197,14 +196,14 @@ SF3D_HD void sf3d_row_node_phase(const SF3DView &v, uint32_t i, double dt, int w
         const double Se = v.Se[i];
         // computeNodeK (soilPhysics.cpp:164-172)
         K = sf3d_mualem(s, v.wrcModel, Se);
-        if (HEAT && v.computeHeatVapor) K += sf3d_heat_vapor_K(v, i);
+        double dThetadH = 0., dThetaVdH = 0.;
+        if (withCapacity) dThetadH = sf3d_dtheta_dh(s, v.wrcModel, H, oldH, z, Se, v.SeOld[i]);
+        if (HEAT) K = sf3d_heat_node_water(v, i, s, H, z, Se, K, withCapacity ? &dThetadH : nullptr, &dThetaVdH);
         v.K[i] = K;
-        if (HEAT && v.computeHeatVapor) v.hTVK[i] = sf3d_heat_water_tvk(v, i);     // read by both ends of every link
         if (withCapacity)
         {
-            const double dThetadH = sf3d_dtheta_dh(s, v.wrcModel, H, oldH, z, Se, v.SeOld[i]);
             double c = v.size[i] * dThetadH;
-            if (HEAT && v.computeHeatVapor) c += v.size[i] * sf3d_heat_dthetav_dh(v, i, dThetadH);
+            if (HEAT && v.computeHeatVapor) c += v.size[i] * dThetaVdH;
             v.cap[i] = c;
         }
     }
@@ -380,7 +379,8 @@ SF3D_HD double sf3d_runoff(const SF3DView &v, uint32_t i, uint32_t j, int approx
     return Kij;
 }
 
-SF3D_HD double sf3d_heat_thermal_invariant(const SF3DView &v, uint32_t i, int slot, uint32_t j);   // water.cpp:329-340
+SF3D_HD double sf3d_heat_thermal_invariant(const SF3DView &v, uint32_t i, int slot, double tli, double tvi, double tmi,
+                                          double tlj, double tvj, double tmj);   // water.cpp:329-340
 
 // ==========================================================================================
 // assembly of one row: CPUSolver::computeLinearSystemElement + computeDiagonalElement +
@@ -450,11 +450,14 @@ SF3D_HD double sf3d_row_assemble_soil(const SF3DView &v, uint32_t i, double dt, 
     const double ki = v.K[i];
     const int32_t *off = sf3d_row_pattern(v, i);
     double sum = 0., invariant = 0.;
+    double tli = 0., tvi = 0., tmi = 0.;
+    if (HEAT) { tli = v.hTLK[i]; tmi = v.hTm[i]; if (v.computeHeatVapor) tvi = v.hTVK[i]; }
     #pragma unroll
     for (int half = 0; half < 2; ++half)
     {
         uint32_t j[5];
         double g[5], kj[5];
+        double tl[5], tv[5], tm[5];
         #pragma unroll
         for (int q = 0; q < 5; ++q)
         {
@@ -464,6 +467,15 @@ SF3D_HD double sf3d_row_assemble_soil(const SF3DView &v, uint32_t i, double dt, 
         }
         #pragma unroll
         for (int q = 0; q < 5; ++q) kj[q] = v.K[j[q]];
+        if (HEAT)
+        {
+            #pragma unroll
+            for (int q = 0; q < 5; ++q)
+            {
+                tl[q] = v.hTLK[j[q]]; tm[q] = v.hTm[j[q]];
+                tv[q] = v.computeHeatVapor ? v.hTVK[j[q]] : 0.;
+            }
+        }
         #pragma unroll
         for (int q = 0; q < 5; ++q)
         {
@@ -480,7 +492,7 @@ SF3D_HD double sf3d_row_assemble_soil(const SF3DView &v, uint32_t i, double dt, 
                 const double area = 0.;
 #endif
                 kc = sf3d_redistribution(v, ki, kj[q], slot, area, g[q]);
-                if (HEAT && j[q] != i) invariant += sf3d_heat_thermal_invariant(v, i, slot, j[q]);
+                if (HEAT && j[q] != i) invariant += sf3d_heat_thermal_invariant(v, i, slot, tli, tvi, tmi, tl[q], tv[q], tm[q]);
             }
             k[c * kstride] = kc;
             sum += kc;                                    // zero entries are not stored in the reference; +0 is exact

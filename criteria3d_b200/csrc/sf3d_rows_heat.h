@@ -27,6 +27,25 @@
 #define HC_VAPOR_DIFFUSIVITY0 0.0000212
 #define HC_THETAMIN 0.15
 
+#ifndef SF3D_HEAT_LINK_UNROLL
+#define SF3D_HEAT_LINK_UNROLL 1      // link loops of the heat rows
+#endif
+constexpr int kHeatLinkUnroll = SF3D_HEAT_LINK_UNROLL;
+
+// pow() with the small integer exponents heat.cpp passes: the product multiplies, the reference-rounding
+// build calls the library like the reference does
+#if defined(__CUDA_ARCH__) && !defined(SF3D_REFERENCE_ROUNDING)
+SF3D_HD double h_pow1(double x) { return x; }
+SF3D_HD double h_pow2(double x) { return x * x; }
+SF3D_HD double h_pow3(double x) { return x * x * x; }
+SF3D_HD double h_pow4(double x) { const double x2 = x * x; return x2 * x2; }
+#else
+SF3D_HD double h_pow1(double x) { return pow(x, 1.); }
+SF3D_HD double h_pow2(double x) { return pow(x, 2.); }
+SF3D_HD double h_pow3(double x) { return pow(x, 3); }
+SF3D_HD double h_pow4(double x) { return pow(x, 4); }
+#endif
+
 // ---- small closures (heat.cpp:1043-1250) ----------------------------------------------------
 SF3D_HD double h_latent_vaporization(double Tc) { return (2501000. - 2369.2 * Tc); }                    // :1085
 SF3D_HD double h_sat_vapor_pressure(double Tc) { return 611 * exp(17.502 * Tc / (Tc + 240.97)); }       // :1164
@@ -41,15 +60,16 @@ SF3D_HD double h_vapor_from_psi_temp(double h, double T)                        
     return svc * rh;
 }
 SF3D_HD double h_pressure_from_altitude(double height)                                                    // :1117
-{ return HC_P0 * pow(1 + height * HC_LAPSE_RATE_MOIST_AIR / HC_TP0, -HC_GRAVITY / (HC_LAPSE_RATE_MOIST_AIR * HC_R_DRY_AIR)); }
+{ return HC_P0 * sf3d_pow(1 + height * HC_LAPSE_RATE_MOIST_AIR / HC_TP0, -HC_GRAVITY / (HC_LAPSE_RATE_MOIST_AIR * HC_R_DRY_AIR)); }
 SF3D_HD double h_air_molar_density(double p, double T) { return 44.65 * (p / HC_P0) * (HC_ZEROCELSIUS / T); }   // :1186
 SF3D_HD double h_air_vol_specific_heat(double p, double T) { return HC_HEAT_CAPACITY_AIR_MOLAR * h_air_molar_density(p, T); }   // :1197
 SF3D_HD double h_svp_slope(double Tc, double svp) { return (4098. * svp / ((237.3 + Tc) * (237.3 + Tc))); }   // :1175
-SF3D_HD double h_vapor_binary_diffusivity(double T) { return HC_VAPOR_DIFFUSIVITY0 * pow(T / HC_ZEROCELSIUS, 2.); }   // :1230
+SF3D_HD double h_vapor_binary_diffusivity(double T) { return HC_VAPOR_DIFFUSIVITY0 * h_pow2(T / HC_ZEROCELSIUS); }   // :1230
 SF3D_HD double h_soil_vapor_diffusivity(double thetaS, double theta, double T)                            // :1127
 {
     const double beta = 0.66, m = 1.;
-    return h_vapor_binary_diffusivity(T) * beta * pow(thetaS - theta, m);
+    (void)m;
+    return h_vapor_binary_diffusivity(T) * beta * h_pow1(thetaS - theta);
 }
 SF3D_HD double h_soil_surface_resistance(double thetaTop) { return 10 * exp(0.3563 * (HC_THETAMIN - thetaTop) * 100); }   // :1154
 SF3D_HD double h_water_return_flow_factor(double theta, double T, double clay)                            // :1097
@@ -57,8 +77,8 @@ SF3D_HD double h_water_return_flow_factor(double theta, double T, double clay)  
     const double wc0 = 0.078 + 0.33 * clay;
     if (theta < 0.01 * wc0) return 0.;
     const double q0 = 2.52 + 7.25 * clay;
-    const double q = q0 * pow(T / 303., 2.);
-    return 1. / (1. + pow(theta / wc0, -q));
+    const double q = q0 * h_pow2(T / 303.);
+    return 1. / (1. + sf3d_pow(theta / wc0, -q));
 }
 SF3D_HD double h_thermal_liquid_conductivity(double Tc, double h, double ILK)                             // :1242
 {
@@ -79,54 +99,55 @@ SF3D_HD double h_theta(const SF3DView &v, uint32_t i, double signedPsi)         
 { return (i < v.Ns) ? 1. : sf3d_theta_from_signed_psi(h_soil(v, i), v.wrcModel, signedPsi); }
 SF3D_HD double h_mean_T(const SF3DView &v, uint32_t i) { return (v.T[i] + v.oldT[i]) * 0.5; }   // getNodeMeanTemperature, soilPhysics.cpp:305-311
 
-// computeNodeThermalVaporConductivity (heat.cpp:780-819)
-SF3D_HD double h_thermal_vapor_conductivity(const SF3DView &v, uint32_t i, double T, double h)
+// The vapour closures of one node share their sub-expressions (saturation vapour pressure and
+// concentration, soil relative humidity, vapour diffusivity): evaluated once per (node, T, h) here, the
+// closures below combine them with the reference's own operations in the reference's order.
+struct HeatNodeCtx { double T, theta, svp, svc, rh, vConc, vDiff; };
+SF3D_HD HeatNodeCtx h_node_ctx(const SoilRec &s, double T, double h, double theta)
 {
-    const SoilRec &s = h_soil(v, i);
-    const double Tc = T - HC_ZEROCELSIUS;
-    const double aPressure = h_pressure_from_altitude(v.z[i]);
-    const double theta = h_theta(v, i, h);
-    const double vDiff = h_soil_vapor_diffusivity(s.thetaS, theta, T);
-    const double svPressure = h_sat_vapor_pressure(Tc);
-    const double svpSlope = h_svp_slope(Tc, svPressure / 1000);
-    const double svcSlope = svpSlope * HC_MH2O * h_air_molar_density(aPressure, T) / aPressure;
-    const double vConc = h_vapor_from_psi_temp(h, T);
-    const double vPressure = h_vapor_pressure_from_conc(vConc, T);
-    const double rH = vPressure / svPressure;
-    const double satDegree = theta / s.thetaS;
-    const double eta = 9.5 + 3. * satDegree - 8.5 * exp(-pow((1. + 2.6 / sqrt(s.clay)) * satDegree, 4));
-    return eta * vDiff * svcSlope * rH;
+    HeatNodeCtx c;
+    c.T = T; c.theta = theta;
+    c.svp = h_sat_vapor_pressure(T - HC_ZEROCELSIUS);
+    c.svc = h_vapor_conc_from_pressure(c.svp, T);
+    c.rh = h_soil_relative_humidity(h, T);
+    c.vConc = c.svc * c.rh;                                          // VaporFromPsiTemp, heat.cpp:1071
+    c.vDiff = h_soil_vapor_diffusivity(s.thetaS, theta, T);
+    return c;
+}
+// computeNodeThermalVaporConductivity (heat.cpp:780-819); aPressure = pressureFromAltitude(z)
+SF3D_HD double h_tvk(const SoilRec &s, const HeatNodeCtx &c, double aPressure)
+{
+    const double Tc = c.T - HC_ZEROCELSIUS;
+    const double svpSlope = h_svp_slope(Tc, c.svp / 1000);
+    const double svcSlope = svpSlope * HC_MH2O * h_air_molar_density(aPressure, c.T) / aPressure;
+    const double vPressure = h_vapor_pressure_from_conc(c.vConc, c.T);
+    const double rH = vPressure / c.svp;
+    const double satDegree = c.theta / s.thetaS;
+    const double eta = 9.5 + 3. * satDegree - 8.5 * exp(-h_pow4(s.etaClay * satDegree));
+    return eta * c.vDiff * svcSlope * rH;
 }
 // computeNodeIsothermalVaporConductivity (heat.cpp:827-841)
-SF3D_HD double h_isothermal_vapor_conductivity(const SF3DView &v, uint32_t i, double T, double h)
-{
-    const SoilRec &s = h_soil(v, i);
-    const double theta = h_theta(v, i, h);
-    const double vDiff = h_soil_vapor_diffusivity(s.thetaS, theta, T);
-    const double vConc = h_vapor_from_psi_temp(h, T);
-    return (vDiff * vConc * HC_MH2O) / (HC_R_GAS * T);
-}
+SF3D_HD double h_ivk(const HeatNodeCtx &c) { return (c.vDiff * c.vConc * HC_MH2O) / (HC_R_GAS * c.T); }
 // computeNodeHeatAirConductivity (heat.cpp:752-772); computeWater is always true on this path
-SF3D_HD double h_air_conductivity(const SF3DView &v, uint32_t i, double T, double h)
+SF3D_HD double h_air_conductivity(double T, double tvk)
 {
     const double Tc = T - HC_ZEROCELSIUS;
     double aK = 0.024 + 0.0000773 * Tc - 0.000000026 * Tc * Tc;
     const double lambda = h_latent_vaporization(Tc);
-    const double niVK = h_thermal_vapor_conductivity(v, i, T, h);
-    aK += lambda * niVK;
+    aK += lambda * tvk;
     return aK;
 }
-// computeNodeHeatSoilConductivity (heat.cpp:702-744)
-SF3D_HD double h_soil_heat_conductivity(const SF3DView &v, uint32_t i, double T, double h)
+// computeNodeHeatSoilConductivity (heat.cpp:702-744); tvk = thermal vapour conductivity at (T, h)
+SF3D_HD double h_soil_heat_conductivity(const SoilRec &s, const HeatNodeCtx &c, double tvk)
 {
-    const SoilRec &s = h_soil(v, i);
+    const double T = c.T;
     const double Tc = T - HC_ZEROCELSIUS;
-    const double wVol = h_theta(v, i, h);
+    const double wVol = c.theta;
     const double sVol = 1. - s.thetaS;
     const double aVol = s.thetaS - wVol;
     const double wRet = h_water_return_flow_factor(wVol, T, s.clay);
     const double wK = 0.554 + 0.0024 * Tc - 0.00000987 * Tc * Tc;
-    const double aK = h_air_conductivity(v, i, T, h);
+    const double aK = h_air_conductivity(T, tvk);
     const double fK = aK + wRet * (wK - aK);
     const double ga = 0.088;
     const double gc = 1. - 2. * ga;
@@ -134,6 +155,20 @@ SF3D_HD double h_soil_heat_conductivity(const SF3DView &v, uint32_t i, double T,
     const double wW = (2. / (1. + (wK / fK - 1.) * ga) + 1. / (1. + (wK / fK - 1.) * gc)) / 3.;
     const double sW = (2. / (1. + (HC_MINERAL_HK / fK - 1.) * ga) + 1. / (1. + (HC_MINERAL_HK / fK - 1.) * gc)) / 3.;
     return (wVol * wW * wK + aVol * aW * aK + sVol * sW * HC_MINERAL_HK) / (wW * wVol + aW * aVol + sW * sVol);
+}
+// the same closures from (node, T, h), as the reference calls them.  The per-node pressure table lives on
+// the device; the host getters (views over host mirrors, hPress == null) evaluate the closure
+SF3D_HD double h_node_pressure(const SF3DView &v, uint32_t i) { return v.hPress ? v.hPress[i] : h_pressure_from_altitude(v.z[i]); }
+SF3D_HD double h_thermal_vapor_conductivity(const SF3DView &v, uint32_t i, double T, double h)
+{
+    const SoilRec &s = h_soil(v, i);
+    return h_tvk(s, h_node_ctx(s, T, h, h_theta(v, i, h)), h_node_pressure(v, i));
+}
+SF3D_HD double h_soil_heat_conductivity(const SF3DView &v, uint32_t i, double T, double h)
+{
+    const SoilRec &s = h_soil(v, i);
+    const HeatNodeCtx c = h_node_ctx(s, T, h, h_theta(v, i, h));
+    return h_soil_heat_conductivity(s, c, h_tvk(s, c, h_node_pressure(v, i)));
 }
 // computeNodeVaporThetaV (heat.cpp:868-875)
 SF3D_HD double h_vapor_theta_v(const SF3DView &v, uint32_t i, double h, double T)
@@ -170,29 +205,53 @@ SF3D_HD double h_distance3d(const SF3DView &v, uint32_t i, uint32_t j)          
     double n = 0; n += dx * dx; n += dy * dy; n += dz * dz;
     return sqrt(n);
 }
+// static heat geometry, filled once per topology: ldist3[slot][i] and hPress[i]
+SF3D_HD void sf3d_row_heat_geometry(const SF3DView &v, uint32_t i)
+{
+    const size_t N = v.N;
+    const uint32_t m = v.meta[i];
+    v.hPress[i] = h_pressure_from_altitude(v.z[i]);
+    for (int slot = 0; slot < SF3D_NLINK; ++slot)
+        v.ldist3[(size_t)slot * N + i] = META_HAS_SLOT(m, slot) ? h_distance3d(v, i, v.lidx[(size_t)slot * N + i]) : 1.;
+}
+SF3D_HD double h_link_distance3d(const SF3DView &v, uint32_t i, int slot) { return SF3D_LDS(v.ldist3 + (size_t)slot * v.N + i); }
 
 // ---- water-side hooks --------------------------------------------------------------------------
-// computeNodeK's vapour term (soilPhysics.cpp:168-169)
+// computeNodeK's vapour term (soilPhysics.cpp:168-169) from the node's current state (bulk potential setter)
 SF3D_HD double sf3d_heat_vapor_K(const SF3DView &v, uint32_t i)
-{ return h_isothermal_vapor_conductivity(v, i, h_mean_T(v, i), v.H[i] - v.z[i]) * (HC_GRAVITY / HC_WATER_DENSITY); }
-
-// computeNodedThetaVdH (soilPhysics.cpp:287-299), temperature = node mean temperature (water.cpp:294)
-SF3D_HD double sf3d_heat_dthetav_dh(const SF3DView &v, uint32_t i, double dThetadH)
+{
+    const SoilRec &s = h_soil(v, i);
+    const double T = h_mean_T(v, i), h = v.H[i] - v.z[i];
+    return h_ivk(h_node_ctx(s, T, h, h_theta(v, i, h))) * (HC_GRAVITY / HC_WATER_DENSITY);
+}
+// One call per soil node and Picard approximation, with the processType::Water arguments (node mean
+// temperature, current matric potential; theta from the stored Se, which is the value
+// computeNodeTheta_fromSignedPsi recomputes).  Adds the vapour term of computeNodeK
+// (soilPhysics.cpp:168-169) to K, stores what the link loop of the assembly reads from both ends of
+// every link (mean T, thermal liquid / vapour conductivity) and returns computeNodedThetaVdH
+// (soilPhysics.cpp:287-299) through *dThetaVdH when dThetadH is given.
+SF3D_HD double sf3d_heat_node_water(const SF3DView &v, uint32_t i, const SoilRec &s, double H, double z, double Se, double K,
+                                   const double *dThetadH, double *dThetaVdH)
 {
     const double T = h_mean_T(v, i);
-    const double h = v.H[i] - v.z[i];
-    const double rH = h_soil_relative_humidity(h, T);
-    const double satVP = h_sat_vapor_pressure(T - HC_ZEROCELSIUS);
-    const double satVC = h_vapor_conc_from_pressure(satVP, T);
-    const double theta = h_theta(v, i, h);
-    const double dThetaVdPsi = (satVC * rH / HC_WATER_DENSITY) * ((h_soil(v, i).thetaS - theta) * HC_MH2O / (HC_R_GAS * T) - dThetadH / HC_GRAVITY);
-    return dThetaVdPsi * HC_GRAVITY;
+    const double h = H - z;
+    if (v.computeHeatVapor)
+    {
+        const double theta = (h >= 0.) ? s.thetaS : sf3d_theta_from_se(s, Se);
+        const HeatNodeCtx c = h_node_ctx(s, T, h, theta);
+        K += h_ivk(c) * (HC_GRAVITY / HC_WATER_DENSITY);
+        v.hTVK[i] = h_tvk(s, c, v.hPress[i]);
+        if (dThetadH)
+        {
+            const double dThetaVdPsi = (c.svc * c.rh / HC_WATER_DENSITY) * ((s.thetaS - theta) * HC_MH2O / (HC_R_GAS * T) - *dThetadH / HC_GRAVITY);
+            *dThetaVdH = dThetaVdPsi * HC_GRAVITY;
+        }
+    }
+    v.hTm[i] = T;
+    v.hTLK[i] = h_thermal_liquid_conductivity(T - HC_ZEROCELSIUS, h, K);
+    return K;
 }
 
-// per-node thermal vapour conductivity with the processType::Water arguments (mean temperature,
-// current matric potential): stored by the node phase, read by both ends of every link in the assembly
-SF3D_HD double sf3d_heat_water_tvk(const SF3DView &v, uint32_t i)
-{ return h_thermal_vapor_conductivity(v, i, h_mean_T(v, i), v.H[i] - v.z[i]); }
 // per-node coefficients with the processType::Heat arguments (node temperature, head averaged over the
 // heat sub-step): stored by sf3d_row_heat_coeffs before the flux snapshot and before every heat assembly
 SF3D_HD void sf3d_row_heat_coeffs(const SF3DView &v, uint32_t i, double dtHeat, double dtWater)
@@ -200,64 +259,52 @@ SF3D_HD void sf3d_row_heat_coeffs(const SF3DView &v, uint32_t i, double dtHeat, 
     if (i < v.Ns) return;
     const double avgH = (h_H_from_steps(v, i, dtHeat, dtWater) + v.oldH[i]) * 0.5 - v.z[i];
     const double T = v.T[i];
-    v.hCond[i] = h_soil_heat_conductivity(v, i, T, avgH);
-    v.hIVK[i] = h_isothermal_vapor_conductivity(v, i, T, avgH);
-    v.hTVK[i] = h_thermal_vapor_conductivity(v, i, T, avgH);
+    const SoilRec &s = h_soil(v, i);
+    const HeatNodeCtx c = h_node_ctx(s, T, avgH, h_theta(v, i, avgH));
+    const double tvk = h_tvk(s, c, v.hPress[i]);
+    v.hCond[i] = h_soil_heat_conductivity(s, c, tvk);
+    v.hIVK[i] = h_ivk(c);
+    v.hTVK[i] = tvk;
+    // computeThermalLiquidFlux, processType::Heat (heat.cpp:458-500): its head is the sub-step average only
+    // when the heat step differs from the water step
+    const double liquidH = (dtHeat != dtWater) ? avgH : (v.H[i] + v.oldH[i]) * 0.5 - v.z[i];
+    v.hTLKh[i] = h_thermal_liquid_conductivity(T - HC_ZEROCELSIUS, liquidH, v.K[i]);
 }
 
-// computeThermalLiquidFlux / computeThermalVaporFlux (heat.cpp:458-553); forWater selects the
-// processType::Water branch (mean temperatures, current heads) or the Heat branch
-SF3D_HD void h_thermal_operands(const SF3DView &v, uint32_t i, uint32_t j, bool forWater, bool liquid, double dtHeat, double dtWater,
-                               double &srcT, double &dstT, double &srcH, double &dstH)
+// computeThermalLiquidFlux / computeThermalVaporFlux (heat.cpp:458-553), processType::Heat branch: node
+// temperatures, conductivities stored per node by sf3d_row_heat_coeffs with exactly these arguments
+SF3D_HD double h_thermal_liquid_flux_heat(const SF3DView &v, uint32_t i, int slot, uint32_t j)
 {
-    if (forWater)
-    {
-        srcT = h_mean_T(v, i); dstT = h_mean_T(v, j);
-        srcH = v.H[i] - v.z[i]; dstH = v.H[j] - v.z[j];
-    }
-    else
-    {
-        srcT = v.T[i]; dstT = v.T[j];
-        if (!liquid || dtHeat != dtWater)
-        {
-            srcH = (h_H_from_steps(v, i, dtHeat, dtWater) + v.oldH[i]) * 0.5 - v.z[i];
-            dstH = (h_H_from_steps(v, j, dtHeat, dtWater) + v.oldH[j]) * 0.5 - v.z[j];
-        }
-        else
-        {
-            srcH = (v.H[i] + v.oldH[i]) * 0.5 - v.z[i];
-            dstH = (v.H[j] + v.oldH[j]) * 0.5 - v.z[j];
-        }
-    }
-}
-SF3D_HD double h_thermal_liquid_flux(const SF3DView &v, uint32_t i, int slot, uint32_t j, bool forWater, double dtHeat, double dtWater)
-{
-    double srcT, dstT, srcH, dstH;
-    h_thermal_operands(v, i, j, forWater, true, dtHeat, dtWater, srcT, dstT, srcH, dstH);
-    const double a = h_thermal_liquid_conductivity(srcT - HC_ZEROCELSIUS, srcH, v.K[i]);
-    const double b = h_thermal_liquid_conductivity(dstT - HC_ZEROCELSIUS, dstH, v.K[j]);
-    const double avg = sf3d_mean(a, b, 2);                        // computeMean default = Logarithmic
-    const double density = avg * (dstT - srcT) / h_distance3d(v, i, j);
+    const double avg = sf3d_mean(v.hTLKh[i], v.hTLKh[j], 2);     // computeMean default = Logarithmic
+    const double density = avg * (v.T[j] - v.T[i]) / h_link_distance3d(v, i, slot);
     return density * v.larea[(size_t)slot * v.N + i];
 }
-// usePre: the two conductivities were stored per node (v.hTVK) by the pass that precedes the caller,
-// evaluated with exactly the arguments computed here
-SF3D_HD double h_thermal_vapor_flux(const SF3DView &v, uint32_t i, int slot, uint32_t j, bool forWater, double dtHeat, double dtWater,
-                                   bool usePre = false)
+SF3D_HD double h_thermal_vapor_flux_heat(const SF3DView &v, uint32_t i, int slot, uint32_t j, double dtHeat, double dtWater, bool usePre)
 {
-    double srcT, dstT, srcH, dstH;
-    h_thermal_operands(v, i, j, forWater, false, dtHeat, dtWater, srcT, dstT, srcH, dstH);
-    const double a = usePre ? v.hTVK[i] : h_thermal_vapor_conductivity(v, i, srcT, srcH);
-    const double b = usePre ? v.hTVK[j] : h_thermal_vapor_conductivity(v, j, dstT, dstH);
+    double a, b;
+    if (usePre) { a = v.hTVK[i]; b = v.hTVK[j]; }
+    else
+    {
+        const double srcH = (h_H_from_steps(v, i, dtHeat, dtWater) + v.oldH[i]) * 0.5 - v.z[i];
+        const double dstH = (h_H_from_steps(v, j, dtHeat, dtWater) + v.oldH[j]) * 0.5 - v.z[j];
+        a = h_thermal_vapor_conductivity(v, i, v.T[i], srcH);
+        b = h_thermal_vapor_conductivity(v, j, v.T[j], dstH);
+    }
     const double avg = sf3d_mean(a, b, 2);
-    const double density = avg * (dstT - srcT) / h_distance3d(v, i, j);
+    const double density = avg * (v.T[j] - v.T[i]) / h_link_distance3d(v, i, slot);
     return density * v.larea[(size_t)slot * v.N + i];
 }
 // water.cpp:329-340: thermal liquid (+ vapour / rho_w) flux added to the row's invariant fluxes
-SF3D_HD double sf3d_heat_thermal_invariant(const SF3DView &v, uint32_t i, int slot, uint32_t j)
+// (processType::Water branch).  tl / tv / tm: thermal liquid conductivity, thermal vapour conductivity
+// and mean temperature of the two ends, stored by sf3d_heat_node_water.
+SF3D_HD double sf3d_heat_thermal_invariant(const SF3DView &v, uint32_t i, int slot, double tli, double tvi, double tmi,
+                                          double tlj, double tvj, double tmj)
 {
-    double f = h_thermal_liquid_flux(v, i, slot, j, true, 0., 0.);
-    if (v.computeHeatVapor) f += h_thermal_vapor_flux(v, i, slot, j, true, 0., 0., true) / HC_WATER_DENSITY;
+    const double d3 = h_link_distance3d(v, i, slot);
+    const double area = SF3D_LDS(v.larea + (size_t)slot * v.N + i);
+    const double dT = tmj - tmi;
+    double f = (sf3d_mean(tli, tlj, 2) * dT / d3) * area;
+    if (v.computeHeatVapor) f += ((sf3d_mean(tvi, tvj, 2) * dT / d3) * area) / HC_WATER_DENSITY;
     return f;
 }
 
@@ -350,7 +397,7 @@ SF3D_HD double h_aerodynamic_conductance(const SF3DView &v, uint32_t i)
         const double uStar = HC_VON_KARMAN * wind / (log((heightWind - zeroPlane + rMomentum) / rMomentum) + psiM);
         K = HC_VON_KARMAN * uStar / (log((heightT - zeroPlane + rHeat) / rHeat) + psiH);
         const double Hf = K * cH * (soilT - airT);
-        const double sP = -HC_VON_KARMAN * heightWind * HC_GRAVITY * Hf / (cH * airT * (pow(uStar, 3)));
+        const double sP = -HC_VON_KARMAN * heightWind * HC_GRAVITY * Hf / (cH * airT * (h_pow3(uStar)));
         if (sP > 0) { psiH = 6 * log(1 + sP); psiM = psiH; }
         else { psiH = -2 * log((1 + sqrt(1 - 16 * sP)) / 2); psiM = 0.6 * psiH; }
         if (first) first = false;
@@ -379,13 +426,13 @@ SF3D_HD double h_isothermal_vapor_flux(const SF3DView &v, uint32_t i, int slot, 
     const double avg = sf3d_mean(a, b, 2);
     const double srcPsi = srcH * HC_GRAVITY, dstPsi = dstH * HC_GRAVITY;
     const double deltaPsi = dstPsi - srcPsi;
-    return avg * deltaPsi / h_distance3d(v, i, j) * v.larea[(size_t)slot * v.N + i];
+    return avg * deltaPsi / h_link_distance3d(v, i, slot) * v.larea[(size_t)slot * v.N + i];
 }
 SF3D_HD void sf3d_row_save_water_fluxes(const SF3DView &v, uint32_t i, double dtHeat, double dtWater)
 {
     const size_t N = v.N;
     const uint32_t m = v.meta[i];
-    #pragma unroll 1
+    #pragma unroll kHeatLinkUnroll
     for (int slot = 0; slot < SF3D_NLINK; ++slot)
     {
         if (!META_HAS_SLOT(m, slot)) continue;
@@ -397,8 +444,8 @@ SF3D_HD void sf3d_row_save_water_fluxes(const SF3DView &v, uint32_t i, double dt
         const double isoLiquid = A * (srcAvgH - dstAvgH);
         const bool deep = !(i < v.Ns) && !(j < v.Ns);
         const double isoVapor = deep ? h_isothermal_vapor_flux(v, i, slot, j, dtHeat, dtWater) : 0.;
-        const double thLiquid = deep ? h_thermal_liquid_flux(v, i, slot, j, false, dtHeat, dtWater) : 0.;
-        const double thVapor = deep ? h_thermal_vapor_flux(v, i, slot, j, false, dtHeat, dtWater, true) : 0.;
+        const double thLiquid = deep ? h_thermal_liquid_flux_heat(v, i, slot, j) : 0.;
+        const double thVapor = deep ? h_thermal_vapor_flux_heat(v, i, slot, j, dtHeat, dtWater, true) : 0.;
         v.lwFlux[li] = (double)(float)(isoLiquid - isoVapor / HC_WATER_DENSITY + thLiquid);
         v.lvFlux[li] = (double)(float)(isoVapor + thVapor);
         if (v.hfSaveMode == 2)
@@ -431,7 +478,7 @@ SF3D_HD double sf3d_row_boundary_heat(const SF3DView &v, uint32_t i, double maxT
             const uint32_t up = v.lidx[i];
             if (up < v.Ns)
             {
-                const double pressure = h_pressure_from_altitude(v.z[i]);
+                const double pressure = v.hPress[i];
                 const double deltaT = v.hbT[i] - v.T[i];
                 sens += h_air_vol_specific_heat(pressure, v.hbT[i]) * deltaT * v.hbAero[i];
             }
@@ -508,7 +555,7 @@ SF3D_HD void h_save_specific_flux(const SF3DView &v, uint32_t i, int slot, int t
 // Heat::conduction (heat.cpp:643-661)
 SF3D_HD double h_conduction(const SF3DView &v, uint32_t i, int slot, uint32_t j, double dtHeat, double dtWater)
 {
-    const double zeta = v.larea[(size_t)slot * v.N + i] / h_distance3d(v, i, j);
+    const double zeta = v.larea[(size_t)slot * v.N + i] / h_link_distance3d(v, i, slot);
     (void)dtHeat; (void)dtWater;
     const double nodeK = v.hCond[i];     // = computeNodeHeatSoilConductivity(i, T[i], avgH_i), see sf3d_row_heat_coeffs
     const double linkK = v.hCond[j];
@@ -556,7 +603,7 @@ SF3D_HD void sf3d_row_heat_assemble(const SF3DView &v, uint32_t i, double dtHeat
     const double wf = v.heatWF;
     double sumDP = 0., sumF0 = 0., invariant = 0.;
     double val[SF3D_NLINK];
-    #pragma unroll 1
+    #pragma unroll kHeatLinkUnroll
     for (int slot = 0; slot < SF3D_NLINK; ++slot)
     {
         val[slot] = 0.;
@@ -653,7 +700,7 @@ SF3D_HD void sf3d_row_heat_accept(const SF3DView &v, uint32_t i, double dtHeat, 
             {
                 if (v.computeHeatVapor)
                 {
-                    const double thLatent = h_thermal_vapor_flux(v, i, slot, j, false, dtHeat, dtWater, false) * h_latent_vaporization(v.T[i] - HC_ZEROCELSIUS);
+                    const double thLatent = h_thermal_vapor_flux_heat(v, i, slot, j, dtHeat, dtWater, false) * h_latent_vaporization(v.T[i] - HC_ZEROCELSIUS);
                     h_save_specific_flux(v, i, slot, 3, thLatent);
                     heatDiff -= thLatent;
                 }

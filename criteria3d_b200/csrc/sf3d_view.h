@@ -52,6 +52,7 @@ struct SoilRec {
     double alpha, n, m, he, Sc, thetaS, thetaR, Ksat, L, organicMatter, clay;
     double invM;        // 1 / m                               (soilPhysics.cpp:186)
     double invSc;       // 1 / Sc                              (soilPhysics.cpp:110)
+    double etaClay;     // 1 + 2.6 / sqrt(clay)                (heat.cpp:816)
     double ScPowInvM;   // pow(Sc, 1/m)                        (soilPhysics.cpp:203)
     double tDen;        // 1 - pow(1 - pow(Sc,1/m), m)         (soilPhysics.cpp:206)
 };
@@ -132,6 +133,11 @@ struct SF3DView {
     // per-node coefficients the reference re-evaluates for both ends of every link (same arguments, same
     // value): thermal / isothermal vapour conductivity and soil heat conductivity, computed once per node
     double *hTVK, *hIVK, *hCond;
+    // water-side coupling, stored by the node phase: mean temperature and thermal liquid conductivity
+    // (mean T, current psi); heat side: thermal liquid conductivity (T, sub-step averaged psi)
+    double *hTm, *hTLK, *hTLKh;
+    double *hPress;                 // static: pressureFromAltitude(z), heat.cpp:1117
+    double *ldist3;                 // static: nodeDistance3D per link, slot-major (soilPhysics.cpp:331-335)
     // control / reduction scratch
     Ctrl *ctrl;
     double *partA, *partB, *partC;  // per-block partials

@@ -308,7 +308,9 @@ void *sf3d_ext_stream(void);
  * around every launch while profiling is enabled (bench.py's roofline figures). */
 enum sf3d_kernel {
     SF3D_K_BEGIN_TRY = 0, SF3D_K_NODE_PHASE = 1, SF3D_K_ASSEMBLE = 2, SF3D_K_JACOBI = 3,
-    SF3D_K_POST = 4, SF3D_K_ACCEPT = 5, SF3D_K_OTHER = 6, SF3D_K_COUNT = 7
+    SF3D_K_POST = 4, SF3D_K_ACCEPT = 5, SF3D_K_OTHER = 6,
+    SF3D_K_HEAT_COEFFS = 7, SF3D_K_HEAT_FLUX_SNAPSHOT = 8, SF3D_K_HEAT_BOUNDARY = 9, SF3D_K_HEAT_ASSEMBLE = 10,
+    SF3D_K_HEAT_JACOBI = 11, SF3D_K_HEAT_POST = 12, SF3D_K_HEAT_ACCEPT = 13, SF3D_K_COMM = 14, SF3D_K_COUNT = 15
 };
 typedef struct sf3d_kernel_times {
     double   ms[SF3D_K_COUNT];        /* accumulated device time per kernel kind            */
