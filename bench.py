@@ -11,8 +11,9 @@ hours per wall second are reported beside it.
 
   value : inputs resident in HBM, device time (CUDA events on the library's stream, max over ranks)
   e2e   : the same metric through the C ABI with HOST buffers: every step uploads the forcing
-          (setNodeWaterSinkSource for all nodes, pinned host memory) and reads back the total
-          potential of all nodes; host<->device copies are inside the timed region
+          as the hourly precipitation map (sf3d_ext_set_forcing_rasters = assignPrecipitation +
+          setSinkSource, pinned host memory) and reads back the total potential of all nodes;
+          host<->device copies are inside the timed region
   roofline : Jacobi sweep kernel, algorithmic bytes (12 B per link + 32 B per node) / measured
           kernel time (CUDA events around every launch, same timed region) vs the measured HBM
           copy bandwidth of MEASURED_PEAKS.json
@@ -212,6 +213,9 @@ def main():
     out_host = torch.empty(N, dtype=torch.float64).pin_memory()
     out_np = out_host.numpy()
     assert sf.set_field(Field.WATER_SINK_SOURCE, 0, sink_np) == 0
+    # end-to-end input: the hourly precipitation map [mm h-1], float32 like the reference's meteo maps
+    rain_host = torch.from_numpy(cat.rain_raster(RAIN_MM_H)).pin_memory()
+    rain_np = rain_host.numpy()
 
     def barrier():
         if world > 1:
@@ -246,7 +250,7 @@ def main():
     e0.record(stream)
     sim_e2e = 0.0
     for _ in range(args.steps):
-        sf.set_field(Field.WATER_SINK_SOURCE, 0, sink_np)               # H2D, N doubles
+        sf.set_forcing_rasters(precipitation=rain_np)                   # H2D, rows x cols floats -> sink/source on the device
         sim_e2e += sf.computeStep(3600.0)
         sf.get_field(Field.TOTAL_POTENTIAL, 0, N, out=out_np)           # D2H, N doubles
     e1.record(stream)
@@ -310,7 +314,7 @@ def main():
             "heat_steps": int(c1["heat_steps"] - c0["heat_steps"]), "heat_sweeps": int(c1["heat_sweeps"] - c0["heat_sweeps"]),
             "tries": int(c1["tries"] - c0["tries"]),
             "e2e": {"value": tot_iter_e2e / (ms_e2e * 1e-3), "unit": "node-iterations/s",
-                    "h2d_bytes_per_step": 8 * N, "d2h_bytes_per_step": 8 * N,
+                    "h2d_bytes_per_step": int(rain_np.nbytes), "d2h_bytes_per_step": 8 * N,
                     "ms_per_step": ms_e2e / args.steps, "sim_hours_per_wall_s": sim_e2e / 3600.0 / (ms_e2e * 1e-3)},
             "gpu_launches": int(c1["kernel_launches"] - c0["kernel_launches"]),
             "roofline": {"kernel": "kern_jacobi", "bound": "hbm", "achieved": jac_gbs, "peak": peak, "unit": "GB/s",

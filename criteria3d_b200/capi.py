@@ -141,6 +141,15 @@ class GridDesc(C.Structure):
     ]
 
 
+class ForcingDesc(C.Structure):
+    _fields_ = [
+        ("rows", C.c_uint32), ("cols", C.c_uint32),
+        ("precipitation", C.POINTER(C.c_float)), ("precipitation_nodata", C.c_float),
+        ("n_sink_layers", C.c_uint32), ("layer_sink", C.POINTER(C.c_float)), ("sink_nodata", C.c_float),
+        ("accumulate", C.c_int),
+    ]
+
+
 class Counters(C.Structure):
     _fields_ = [
         ("steps", C.c_uint64), ("tries", C.c_uint64), ("approximations", C.c_uint64),
@@ -242,6 +251,8 @@ _EXT = [
     ("sf3d_ext_get_link_table", u8, [u8, u32, u32, C.POINTER(u8), C.POINTER(u32), C.POINTER(dbl)]),
     ("sf3d_ext_get_node_meta", u8, [u32, u32, C.POINTER(u8), C.POINTER(u8), C.POINTER(u8)]),
     ("sf3d_ext_build_grid", u8, [C.POINTER(GridDesc)]),
+    ("sf3d_ext_set_forcing_rasters", u8, [C.POINTER(ForcingDesc)]),
+    ("sf3d_ext_get_layer_raster", u8, [C.c_int, u32, C.c_float, C.POINTER(C.c_float)]),
     ("sf3d_ext_set_fixed_temperature", u8, [u32, u32, C.POINTER(dbl), dbl]),
     ("sf3d_ext_get_counters", u8, [C.POINTER(Counters)]),
     ("sf3d_ext_reset_counters", u8, []),
@@ -324,6 +335,32 @@ class SoilFluxes3D:
 
     def build_grid(self, desc: GridDesc) -> int:
         return self.lib.sf3d_ext_build_grid(C.byref(desc))
+
+    def set_forcing_rasters(self, precipitation=None, layer_sink=None, *, nodata: float = -9999.0,
+                            accumulate: bool = False) -> int:
+        """Hourly forcing from float rasters [mm h-1] (assignPrecipitation / assignETreal / setSinkSource):
+        precipitation [rows, cols]; layer_sink [n_layers, rows, cols] water removed per layer (0 = surface)."""
+        d = ForcingDesc()
+        keep = []
+        if precipitation is not None:
+            p = np.ascontiguousarray(precipitation, dtype=np.float32); keep.append(p)
+            d.rows, d.cols = p.shape
+            d.precipitation = _ptr(p, C.c_float)
+        if layer_sink is not None:
+            q = np.ascontiguousarray(layer_sink, dtype=np.float32); keep.append(q)
+            d.n_sink_layers, d.rows, d.cols = q.shape
+            d.layer_sink = _ptr(q, C.c_float)
+        d.precipitation_nodata = nodata; d.sink_nodata = nodata
+        d.accumulate = int(accumulate)
+        return self.lib.sf3d_ext_set_forcing_rasters(C.byref(d))
+
+    def get_layer_raster(self, field: int, layer: int, shape, nodata: float = -9999.0) -> np.ndarray:
+        """Output map of one layer (computeCriteria3DMap): float32 [rows, cols]."""
+        out = np.empty(shape, dtype=np.float32)
+        rc = self.lib.sf3d_ext_get_layer_raster(int(field), layer, nodata, _ptr(out, C.c_float))
+        if rc:
+            raise RuntimeError(f"sf3d_ext_get_layer_raster -> {SF3Derror(rc).name}")
+        return out
 
     def set_fixed_temperature(self, first: int, temperature: np.ndarray, depth: float) -> int:
         t = np.ascontiguousarray(temperature, dtype=np.float64)

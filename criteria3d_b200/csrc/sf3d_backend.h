@@ -98,4 +98,19 @@ struct GridDev {
 };
 void k_build_grid(const SF3DView &v, const GridDev &g);
 
+// the raster side of a graph built by sf3d_ext_build_grid: node(layer, cell) = layer * nValid + rank[cell]
+struct RasterDev {
+    uint32_t rows, cols, layers, nValid;
+    double cell;
+    const int32_t *rank;            // rows*cols, -1 outside the catchment
+};
+struct ForcingDev {
+    const float *precipitation; float precipitationNodata;
+    uint32_t nSinkLayers; const float *layerSink; float sinkNodata;
+    int accumulate;
+};
+
+void k_forcing_rasters(const SF3DView &v, const RasterDev &g, const ForcingDev &f);
+void k_layer_raster(const SF3DView &v, const RasterDev &g, int field, uint32_t layer, float nodata, float *dst);
+
 }  // namespace sf3d

@@ -80,6 +80,10 @@ struct State {
     uint16_t *pid = nullptr; int32_t *pattern = nullptr; bool patternsOk = false;
     uint32_t hotPid = 0; int32_t hotOff[SF3D_NLINK] = {0};
     Ctrl *ctrl = nullptr;
+    // raster side of a graph built by sf3d_ext_build_grid (kept for the raster-facing forcing / output calls)
+    RasterDev raster{};
+    int32_t *rasterRank = nullptr;
+    void *rasterStage = nullptr; size_t rasterStageBytes = 0;     // device staging for forcing / output rasters
 
     Engine eng;
 };
@@ -274,6 +278,18 @@ void release_all()
     dev_free(S.mcol); S.mcol = nullptr;
     dev_free(S.pid); S.pid = nullptr; dev_free(S.pattern); S.pattern = nullptr; S.patternsOk = false;
     dev_free(S.ctrl); S.ctrl = nullptr;
+    dev_free(S.rasterRank); S.rasterRank = nullptr; S.raster = RasterDev{};
+    dev_free(S.rasterStage); S.rasterStage = nullptr; S.rasterStageBytes = 0;
+}
+
+void *raster_stage(size_t bytes)
+{
+    if (S.rasterStageBytes < bytes)
+    {
+        dev_free(S.rasterStage); S.rasterStage = nullptr; S.rasterStageBytes = 0;
+        S.rasterStage = dev_alloc(bytes); S.rasterStageBytes = bytes;
+    }
+    return S.rasterStage;
 }
 
 double *scratch_buffer()
@@ -1077,6 +1093,11 @@ uint8_t sf3d_ext_build_grid(const sf3d_grid_desc *g)
         gd.computeWater = S.water; gd.computeHeat = S.heat; gd.heatSurfaceL1 = g->heat_surface_layer1;
         k_build_grid(S.eng.v, gd);
         dev_sync();
+        // the cell -> node map stays on the device for sf3d_ext_set_forcing_rasters / sf3d_ext_get_layer_raster
+        dev_free(S.rasterRank); S.rasterRank = nullptr;
+        for (void *&d : tmp) if (d == (void *)gd.rank) { S.rasterRank = (int32_t *)d; d = nullptr; }
+        S.raster.rows = g->rows; S.raster.cols = g->cols; S.raster.layers = g->layers; S.raster.nValid = g->n_valid;
+        S.raster.cell = g->cell; S.raster.rank = S.rasterRank;
         for (void *d : tmp) dev_free(d);
 
         S.x.dev_written(); S.y.dev_written(); S.z.dev_written(); S.size.dev_written(); S.meta.dev_written();
@@ -1090,6 +1111,58 @@ uint8_t sf3d_ext_build_grid(const sf3d_grid_desc *g)
             for (Mirror<double> *m : heat_boundary_mirrors) m->dev_written();
         }
         S.topoDirty = true;
+        return SF3D_OK;
+    }, (uint8_t)SF3D_MEMORY_ERROR);
+}
+
+// ---- raster-facing forcing / output (semantics in include/sf3d.h) ----------------
+uint8_t sf3d_ext_set_forcing_rasters(const sf3d_forcing_desc *f)
+{
+    return guarded([&]() -> uint8_t {
+        REQUIRE_INIT_E();
+        if (!f) return SF3D_PARAMETER_ERROR;
+        if (!S.rasterRank) return SF3D_MISSING_DATA_ERROR;
+        if (f->rows != S.raster.rows || f->cols != S.raster.cols) return SF3D_PARAMETER_ERROR;
+        if (f->layer_sink && f->n_sink_layers > S.raster.layers) return SF3D_PARAMETER_ERROR;
+        uint8_t rc = sync_to_device();
+        if (rc) return rc;
+        const size_t cells = (size_t)f->rows * f->cols;
+        const size_t nPrec = f->precipitation ? cells : 0, nSink = f->layer_sink ? cells * f->n_sink_layers : 0;
+        float *stage = (float *)raster_stage((nPrec + nSink + 1) * sizeof(float));
+        ForcingDev fd{};
+        if (nPrec) { h2d(stage, f->precipitation, nPrec * sizeof(float)); fd.precipitation = stage; }
+        if (nSink) { h2d(stage + nPrec, f->layer_sink, nSink * sizeof(float)); fd.layerSink = stage + nPrec; }
+        fd.precipitationNodata = f->precipitation_nodata; fd.sinkNodata = f->sink_nodata;
+        fd.nSinkLayers = f->n_sink_layers; fd.accumulate = f->accumulate;
+        S.sink.push();
+        k_forcing_rasters(S.eng.v, S.raster, fd);
+        S.sink.dev_written();
+        return SF3D_OK;
+    }, (uint8_t)SF3D_MEMORY_ERROR);
+}
+
+uint8_t sf3d_ext_get_layer_raster(int field, uint32_t layer, float nodata, float *dst)
+{
+    return guarded([&]() -> uint8_t {
+        REQUIRE_INIT_E();
+        if (!dst) return SF3D_PARAMETER_ERROR;
+        if (!S.rasterRank) return SF3D_MISSING_DATA_ERROR;
+        if (layer >= S.raster.layers) return SF3D_INDEX_ERROR;
+        switch (field)
+        {
+            case SF3D_F_WATER_CONTENT: case SF3D_F_DEGREE_OF_SATURATION: case SF3D_F_WATER_CONDUCTIVITY:
+            case SF3D_F_MATRIC_POTENTIAL: case SF3D_F_TOTAL_POTENTIAL: case SF3D_F_POND:
+            case SF3D_F_BOUNDARY_WATER_FLOW: case SF3D_F_SUM_LATERAL_FLOW: case SF3D_F_MAX_FLOW_UP:
+            case SF3D_F_MAX_FLOW_DOWN: case SF3D_F_MAX_FLOW_LATERAL: case SF3D_F_TEMPERATURE:
+                break;
+            default: return SF3D_PARAMETER_ERROR;
+        }
+        uint8_t rc = sync_to_device();
+        if (rc) return rc;
+        const size_t cells = (size_t)S.raster.rows * S.raster.cols;
+        float *stage = (float *)raster_stage(cells * sizeof(float));
+        k_layer_raster(S.eng.v, S.raster, field, layer, nodata, stage);
+        d2h(dst, stage, cells * sizeof(float));
         return SF3D_OK;
     }, (uint8_t)SF3D_MEMORY_ERROR);
 }

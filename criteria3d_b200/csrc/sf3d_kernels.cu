@@ -22,6 +22,7 @@
 #include <vector>
 #include "sf3d_backend.h"
 #include "sf3d_rows_heat.h"
+#include "sf3d_fields.h"
 
 namespace sf3d {
 
@@ -600,54 +601,23 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_set_potential(SF3DView v, uin
 __global__ void __launch_bounds__(SF3D_BLOCK) kern_get_field(SF3DView v, int field, uint32_t first, uint32_t count,
                                                              double *__restrict__ dst)
 {
-    const size_t N = v.N;
     for (uint32_t k = blockIdx.x * SF3D_BLOCK + threadIdx.x; k < count; k += gridDim.x * SF3D_BLOCK)
-    {
-        const uint32_t i = first + k;
-        const uint32_t m = v.meta[i];
-        const bool surface = META_SURFACE(m);
-        double r = -1111.;
-        switch (field)
-        {
-            case SF3D_F_WATER_CONTENT:
-                r = surface ? (v.H[i] - v.z[i]) : sf3d_theta_from_se(v.soil[v.tab[i]], v.Se[i]);
-                break;
-            case SF3D_F_DEGREE_OF_SATURATION:
-                if (!surface) r = v.Se[i];
-                else
-                {
-                    const double curPot = v.H[i] - v.z[i], maxPot = 0.001;
-                    r = curPot <= 0 ? 0 : (curPot > maxPot ? 1. : curPot / maxPot);
-                }
-                break;
-            case SF3D_F_WATER_CONDUCTIVITY: r = v.K[i]; break;
-            case SF3D_F_MATRIC_POTENTIAL:   r = v.H[i] - v.z[i]; break;
-            case SF3D_F_TOTAL_POTENTIAL:    r = v.H[i]; break;
-            case SF3D_F_POND:               r = surface ? v.pond[i] : -1111.; break;
-            case SF3D_F_BOUNDARY_WATER_FLOW: r = (META_BT(m) == BT_NONE) ? -4444. : v.bSum[i]; break;
-            case SF3D_F_SUM_LATERAL_FLOW:
-            {
-                double s = 0.;
-                for (uint32_t l = 0; l < META_NLAT(m); ++l) s += v.lflow[(size_t)(2 + l) * N + i];
-                r = s;
-                break;
-            }
-            case SF3D_F_MAX_FLOW_UP:   r = v.lflow[i]; break;
-            case SF3D_F_MAX_FLOW_DOWN: r = v.lflow[N + i]; break;
-            case SF3D_F_MAX_FLOW_LATERAL:
-            {
-                double mx = 0.;
-                for (uint32_t l = 0; l < META_NLAT(m); ++l) mx = sf3d_max(mx, v.lflow[(size_t)(2 + l) * N + i]);
-                r = mx;
-                break;
-            }
-            case SF3D_F_TEMPERATURE:
-                r = (v.computeHeat && !surface) ? v.T[i] : -3333.;
-                break;
-            default: break;
-        }
-        dst[k] = r;
-    }
+        dst[k] = sf3d_field_value(v, field, first + k);
+}
+
+// raster-facing forcing / output maps, one thread per raster cell
+__global__ void __launch_bounds__(SF3D_BLOCK) kern_forcing_rasters(SF3DView v, RasterDev g, ForcingDev f)
+{
+    const uint64_t cells = (uint64_t)g.rows * g.cols;
+    for (uint64_t c = (uint64_t)blockIdx.x * SF3D_BLOCK + threadIdx.x; c < cells; c += (uint64_t)gridDim.x * SF3D_BLOCK)
+        sf3d_cell_forcing(v, g, f, c);
+}
+__global__ void __launch_bounds__(SF3D_BLOCK) kern_layer_raster(SF3DView v, RasterDev g, int field, uint32_t layer, float nodata,
+                                                                float *__restrict__ dst)
+{
+    const uint64_t cells = (uint64_t)g.rows * g.cols;
+    for (uint64_t c = (uint64_t)blockIdx.x * SF3D_BLOCK + threadIdx.x; c < cells; c += (uint64_t)gridDim.x * SF3D_BLOCK)
+        dst[c] = sf3d_cell_output(v, g, field, layer, nodata, c);
 }
 
 // DEM -> node/link graph (Project3D::setCrit3DTopography + setCrit3DNodeSoil,
@@ -1235,6 +1205,16 @@ void k_set_potential(const SF3DView &v, uint32_t first, uint32_t count, const do
 { if (count) { kern_set_potential<<<GRID(count)>>>(v, first, count, src, isTotal); LAUNCH_CHECK(); } }
 void k_get_field(const SF3DView &v, int field, uint32_t first, uint32_t count, double *dst)
 { if (count) { kern_get_field<<<GRID(count)>>>(v, field, first, count, dst); LAUNCH_CHECK(); } }
+void k_forcing_rasters(const SF3DView &v, const RasterDev &g, const ForcingDev &f)
+{
+    const uint64_t cells = (uint64_t)g.rows * g.cols;
+    kern_forcing_rasters<<<GRID((uint32_t)(cells > 0xFFFFFFFFull ? 0xFFFFFFFFull : cells))>>>(v, g, f); LAUNCH_CHECK();
+}
+void k_layer_raster(const SF3DView &v, const RasterDev &g, int field, uint32_t layer, float nodata, float *dst)
+{
+    const uint64_t cells = (uint64_t)g.rows * g.cols;
+    kern_layer_raster<<<GRID((uint32_t)(cells > 0xFFFFFFFFull ? 0xFFFFFFFFull : cells))>>>(v, g, field, layer, nodata, dst); LAUNCH_CHECK();
+}
 void k_build_grid(const SF3DView &v, const GridDev &g)
 {
     const uint64_t total = (uint64_t)g.rows * g.cols * g.layers;

@@ -228,6 +228,15 @@ class Catchment:
         q = area * mm_per_hour * scale / 1000.0 / 3600.0
         return np.ascontiguousarray(q.reshape(-1) if self.valid is None else q[np.asarray(self.valid, bool)])
 
+    def rain_raster(self, mm_per_hour: float, nodata: float = -9999.0) -> np.ndarray:
+        """The hourly precipitation map [mm h-1] (float32, as the reference's meteo maps) whose
+        assignPrecipitation result is rain_sink_source up to the float rounding of the map."""
+        c = np.arange(self.cols, dtype=np.float64)[None, :]
+        mm = (mm_per_hour * (1.0 + 0.3 * np.sin(2 * np.pi * c / self.cols)) + np.zeros((self.rows, 1))).astype(np.float32)
+        if self.valid is not None:
+            mm[~np.asarray(self.valid, bool)] = nodata
+        return np.ascontiguousarray(mm)
+
     def initial_matric_potential(self) -> np.ndarray:
         psi = np.full(self.n_nodes, self.initial_psi, np.float64)
         psi[: self.n_surface] = 0.0

@@ -229,6 +229,36 @@ typedef struct sf3d_grid_desc {
 } sf3d_grid_desc;
 uint8_t sf3d_ext_build_grid(const sf3d_grid_desc *desc);
 
+/* Raster-facing forcing and output for a graph built by sf3d_ext_build_grid.
+ *
+ * sf3d_ext_set_forcing_rasters: the hourly forcing assembly of the caller, in the caller's order
+ * (bin/CRITERIA3D/criteria3DProject.cpp:2121-2160): sink/source := 0 on every node (:2123-2127), then
+ * for every valid cell and every layer l < n_sink_layers with s = layer_sink[l][cell] != nodata, s > 0
+ *     sink[node(l, cell)] -= area * (s / 1000.) / 3600.     (assignEvaporation / assignTranspiration,
+ *                                                            src/project3D/project3D.cpp:2397-2401, 2436-2440, 2603)
+ * then with p = precipitation[cell] != nodata, p > 0
+ *     flow = area * (p / 1000.) ; if (flow / 3600. > 0) sink[node(0, cell)] += flow / 3600.
+ *                                                           (assignPrecipitation, criteria3DProject.cpp:939-965)
+ * and Project3D::setSinkSource (project3D.cpp:2269-2285).  Values are float rasters [mm h-1] as the
+ * reference's meteo maps; area = cell * cell.  accumulate != 0 skips the zeroing.
+ * Errors: SF3D_MISSING_DATA_ERROR when no grid was built, SF3D_PARAMETER_ERROR on a shape mismatch. */
+typedef struct sf3d_forcing_desc {
+    uint32_t rows, cols;              /* must equal the built grid                                  */
+    const float *precipitation;       /* rows*cols [mm h-1] liquid water reaching the surface, or NULL */
+    float precipitation_nodata;
+    uint32_t n_sink_layers;           /* layer_sink covers layers 0 .. n_sink_layers-1 (0 = surface) */
+    const float *layer_sink;          /* [n_sink_layers][rows*cols] [mm h-1] water removed, or NULL  */
+    float sink_nodata;
+    int accumulate;
+} sf3d_forcing_desc;
+uint8_t sf3d_ext_set_forcing_rasters(const sf3d_forcing_desc *desc);
+
+/* sf3d_ext_get_layer_raster: Project3D::computeCriteria3DMap (project3D.cpp:1896-1947) for one layer:
+ * dst[cell] = (float) field value of node(layer, cell); nodata for cells outside the catchment and for
+ * values equal to -9999; SF3D_F_WATER_CONTENT on layer 0 is converted from [m] to [mm] (:1936-1940).
+ * dst is a HOST buffer of rows*cols floats. */
+uint8_t sf3d_ext_get_layer_raster(int field, uint32_t layer, float nodata, float *dst);
+
 /* setNodeBoundaryFixedTemperature(i, T[k], depth) for nodes [first, first+count) */
 uint8_t sf3d_ext_set_fixed_temperature(uint32_t first, uint32_t count, const double *temperature, double depth);
 

@@ -214,6 +214,7 @@ double sf3d_compute_step(double maxDt)
 
 /* ---------------- extensions: plain loops over the scalar API ---------------- */
 #include "field_loops.inc"
+#include "raster_loops.inc"
 #include "grid_builder_scalar.inc"
 
 uint8_t sf3d_ext_get_link_table(uint8_t slot, uint32_t first, uint32_t count,

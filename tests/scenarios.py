@@ -175,6 +175,42 @@ def ragged_raster(sf, threads=1):
     return snapshot(sf, cat.n_nodes, dts)
 
 
+def raster_forcing_and_maps(sf, threads=1):
+    """the caller's side of the step through rasters: hourly precipitation map ->
+    sink/source (assignPrecipitation + setSinkSource), then an evapotranspiration hour with per-layer
+    sink maps (assignETreal), then output maps of four layers (computeCriteria3DMap)"""
+    valid = np.ones((20, 17), bool)
+    valid[0:2, 0:4] = False
+    valid[8:10, 6:9] = False
+    cat = Catchment(20, 17, 4, valid=valid)
+    setup(sf, cat, threads=threads)
+    dts = []
+
+    def hour(seconds, budget):
+        t = 0.0
+        while t < seconds and len(dts) < budget:
+            dt = sf.computeStep(seconds - t)
+            dts.append(dt)
+            t += dt
+
+    _ok(sf.set_forcing_rasters(precipitation=cat.rain_raster(25.0)), "forcing rasters (rain)")
+    hour(3600.0, 40)
+    r, c = np.mgrid[0:cat.rows, 0:cat.cols]
+    et = np.zeros((3, cat.rows, cat.cols), np.float32)
+    et[0] = 0.6 + 0.2 * np.cos(r / 3.0)                 # surface evaporation [mm h-1]
+    et[1] = 0.25 + 0.1 * np.sin(c / 2.0)                # first soil layer
+    et[2] = np.where((r + c) % 3 == 0, 0.0, 0.1)        # second soil layer, zeros are skipped
+    et[1, 5, 5] = -9999.0                               # a NODATA cell of the map is skipped
+    _ok(sf.set_forcing_rasters(precipitation=np.zeros((cat.rows, cat.cols), np.float32), layer_sink=et), "forcing rasters (ET)")
+    hour(1800.0, 70)
+    out = snapshot(sf, cat.n_nodes, dts)
+    shape = (cat.rows, cat.cols)
+    out["rasters"] = np.stack([sf.get_layer_raster(Field.WATER_CONTENT, 0, shape), sf.get_layer_raster(Field.WATER_CONTENT, 2, shape),
+                               sf.get_layer_raster(Field.DEGREE_OF_SATURATION, 1, shape), sf.get_layer_raster(Field.TOTAL_POTENTIAL, 4, shape),
+                               sf.get_layer_raster(Field.MATRIC_POTENTIAL, 3, shape)])
+    return out
+
+
 def config1_bundled_catchment(sf, threads=1, hours=8, max_steps=100):
     """BASELINE config 1: the bundled STH sample catchment (DATA/PROJECT/STH/MAPS/DEM_STH.flt, 34 x 139
     cells of 2 m, 1244 NODATA cells; soil map ids 1-3), water only, 2 mm/h rain.  The full 24 h run is
@@ -287,6 +323,7 @@ SCENARIOS = {
     "ragged_raster": ragged_raster,
     "config1_bundled_catchment": config1_bundled_catchment,
     "scalar_api_column": scalar_api_column,
+    "raster_forcing_and_maps": raster_forcing_and_maps,
 }
 HEAT_SCENARIOS = {
     "heat_coupled": heat_coupled,
@@ -335,6 +372,11 @@ def compare(a: dict, b: dict, *, exact: bool, h_rel=1e-6, theta_abs=1e-7, flow_r
         assert np.all(np.abs(hb - hbb) <= 1e-5 * np.abs(hbb) + 1e-9)
         f, fb = a["heat_flux_down"], b["heat_flux_down"]
         assert np.all(np.abs(f - fb) <= 1e-4 * np.abs(fb) + 1e-3)          # float-rounded accumulations (heat.cpp:203-206)
+    if "rasters" in a:
+        # float32 output maps: same NODATA cells, values within float rounding of the fp64 tolerance
+        r, rb = a["rasters"], b["rasters"]
+        assert np.array_equal(r == -9999.0, rb == -9999.0)
+        assert np.all(np.abs(r - rb) <= 2e-6 * np.abs(rb) + 1e-7)
     if "getters" in a:
         g, gb = a["getters"], b["getters"]
         assert np.all(np.abs(g - gb) <= 1e-6 * np.abs(gb) + 1e-12)

@@ -34,6 +34,18 @@ def contract_codes(sf):
             sf.getNodeHeatMaxFlux(soil2, 0, 0), sf.getNodeHeatMaxFlux(soil2, 3, 0),
             sf.getNodeBoundaryWaterFlow(soil2), sf.getNodeMaximumWaterContent(0), sf.getNodeMinimumWaterContent(soil2),
             sf.getNodePond(soil2), sf.getNodePond(1), sf.getNodeWaterDeficit(1, 3.0), sf.getHeatMBR(), sf.getWaterMBR()]
+    # raster-facing extensions: shape mismatch, too many sink layers, layer out of range, unknown field
+    import ctypes as C
+    from criteria3d_b200.capi import ForcingDesc
+    bad = np.zeros((cat.rows + 1, cat.cols), np.float32)
+    out += [sf.set_forcing_rasters(precipitation=bad), sf.set_forcing_rasters(layer_sink=np.zeros((cat.layers + 1, cat.rows, cat.cols), np.float32)),
+            sf.set_forcing_rasters(precipitation=np.zeros((cat.rows, cat.cols), np.float32)), sf.lib.sf3d_ext_set_forcing_rasters(None)]
+    buf = np.zeros((cat.rows, cat.cols), np.float32)
+    P = buf.ctypes.data_as(C.POINTER(C.c_float))
+    out += [sf.lib.sf3d_ext_get_layer_raster(int(Field.WATER_CONTENT), cat.layers, -9999.0, P),
+            sf.lib.sf3d_ext_get_layer_raster(int(Field.WATER_SINK_SOURCE), 0, -9999.0, P),
+            sf.lib.sf3d_ext_get_layer_raster(int(Field.WATER_CONTENT), 0, -9999.0, None),
+            sf.lib.sf3d_ext_get_layer_raster(int(Field.WATER_CONTENT), 0, -9999.0, P)]
     return np.array(out, dtype=np.float64)
 
 
