@@ -12,7 +12,8 @@ hours per wall second are reported beside it.
   value : inputs resident in HBM, device time (CUDA events on the library's stream, max over ranks)
   e2e   : the same metric through the C ABI with HOST buffers: every step uploads the forcing
           as the hourly precipitation map (sf3d_ext_set_forcing_rasters = assignPrecipitation +
-          setSinkSource, pinned host memory) and reads back the total potential of all nodes;
+          setSinkSource, pinned host memory) and reads back the matric potential maps of all
+          layers (sf3d_ext_get_layer_rasters = computeCriteria3DMap per layer, as saveModelsState);
           host<->device copies are inside the timed region
   roofline : Jacobi sweep kernel, algorithmic bytes (12 B per link + 32 B per node) / measured
           kernel time (CUDA events around every launch, same timed region) vs the measured HBM
@@ -210,7 +211,9 @@ def main():
     sink_host = torch.zeros(N, dtype=torch.float64).pin_memory()
     sink_np = sink_host.numpy()
     sink_np[: cat.n_surface] = cat.rain_sink_source(RAIN_MM_H)
-    out_host = torch.empty(N, dtype=torch.float64).pin_memory()
+    # end-to-end output: the matric potential maps of all layers, float32 rasters as saveModelsState /
+    # computeCriteria3DMap produce them
+    out_host = torch.empty((cat.layers, cat.rows, cat.cols), dtype=torch.float32).pin_memory()
     out_np = out_host.numpy()
     assert sf.set_field(Field.WATER_SINK_SOURCE, 0, sink_np) == 0
     # end-to-end input: the hourly precipitation map [mm h-1], float32 like the reference's meteo maps
@@ -245,14 +248,23 @@ def main():
 
     # ---------------- timed region 2: end to end through the C ABI, host buffers ---------------
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sf.set_forcing_rasters(precipitation=rain_np)                       # untimed warm-up of the host-facing calls
+    sf.get_layer_rasters(Field.MATRIC_POTENTIAL, 0, cat.layers, (cat.rows, cat.cols), out=out_np)
+    c1e = sf.counters()
+    tcall = [0.0, 0.0, 0.0]
     barrier()
     t0 = time.perf_counter()
     e0.record(stream)
     sim_e2e = 0.0
     for _ in range(args.steps):
+        ta = time.perf_counter()
         sf.set_forcing_rasters(precipitation=rain_np)                   # H2D, rows x cols floats -> sink/source on the device
+        tb = time.perf_counter()
         sim_e2e += sf.computeStep(3600.0)
-        sf.get_field(Field.TOTAL_POTENTIAL, 0, N, out=out_np)           # D2H, N doubles
+        tc = time.perf_counter()
+        sf.get_layer_rasters(Field.MATRIC_POTENTIAL, 0, cat.layers, (cat.rows, cat.cols), out=out_np)   # D2H, layers x rows x cols floats
+        td = time.perf_counter()
+        tcall[0] += tb - ta; tcall[1] += tc - tb; tcall[2] += td - tc
     e1.record(stream)
     barrier()
     wall_e2e = time.perf_counter() - t0
@@ -261,7 +273,7 @@ def main():
     clk = clocks.stop()
 
     sweeps = c1["sweeps"] - c0["sweeps"]
-    sweeps_e2e = c2["sweeps"] - c1["sweeps"]
+    sweeps_e2e = c2["sweeps"] - c1e["sweeps"]
     t = torch.tensor([ms, ms_e2e, float(sweeps), float(sweeps_e2e), sim, sim_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
         tmax = t.clone()
@@ -314,8 +326,10 @@ def main():
             "heat_steps": int(c1["heat_steps"] - c0["heat_steps"]), "heat_sweeps": int(c1["heat_sweeps"] - c0["heat_sweeps"]),
             "tries": int(c1["tries"] - c0["tries"]),
             "e2e": {"value": tot_iter_e2e / (ms_e2e * 1e-3), "unit": "node-iterations/s",
-                    "h2d_bytes_per_step": int(rain_np.nbytes), "d2h_bytes_per_step": 8 * N,
-                    "ms_per_step": ms_e2e / args.steps, "sim_hours_per_wall_s": sim_e2e / 3600.0 / (ms_e2e * 1e-3)},
+                    "h2d_bytes_per_step": int(rain_np.nbytes), "d2h_bytes_per_step": int(out_np.nbytes),
+                    "ms_per_step": ms_e2e / args.steps,
+                    "host_ms_per_step": {"forcing_upload": 1e3 * tcall[0] / args.steps, "compute_step": 1e3 * tcall[1] / args.steps,
+                                         "result_download": 1e3 * tcall[2] / args.steps}, "sim_hours_per_wall_s": sim_e2e / 3600.0 / (ms_e2e * 1e-3)},
             "gpu_launches": int(c1["kernel_launches"] - c0["kernel_launches"]),
             "roofline": {"kernel": "kern_jacobi", "bound": "hbm", "achieved": jac_gbs, "peak": peak, "unit": "GB/s",
                          "frac": (jac_gbs / peak) if jac_gbs else None, "traffic": traffic, "peak_source": peak_src,

@@ -252,7 +252,7 @@ _EXT = [
     ("sf3d_ext_get_node_meta", u8, [u32, u32, C.POINTER(u8), C.POINTER(u8), C.POINTER(u8)]),
     ("sf3d_ext_build_grid", u8, [C.POINTER(GridDesc)]),
     ("sf3d_ext_set_forcing_rasters", u8, [C.POINTER(ForcingDesc)]),
-    ("sf3d_ext_get_layer_raster", u8, [C.c_int, u32, C.c_float, C.POINTER(C.c_float)]),
+    ("sf3d_ext_get_layer_rasters", u8, [C.c_int, u32, u32, C.c_float, C.POINTER(C.c_float)]),
     ("sf3d_ext_set_fixed_temperature", u8, [u32, u32, C.POINTER(dbl), dbl]),
     ("sf3d_ext_get_counters", u8, [C.POINTER(Counters)]),
     ("sf3d_ext_reset_counters", u8, []),
@@ -356,10 +356,17 @@ class SoilFluxes3D:
 
     def get_layer_raster(self, field: int, layer: int, shape, nodata: float = -9999.0) -> np.ndarray:
         """Output map of one layer (computeCriteria3DMap): float32 [rows, cols]."""
-        out = np.empty(shape, dtype=np.float32)
-        rc = self.lib.sf3d_ext_get_layer_raster(int(field), layer, nodata, _ptr(out, C.c_float))
+        return self.get_layer_rasters(field, layer, 1, shape, nodata)[0]
+
+    def get_layer_rasters(self, field: int, first_layer: int, n_layers: int, shape, nodata: float = -9999.0,
+                          out: np.ndarray | None = None) -> np.ndarray:
+        """Output maps of n_layers consecutive layers: float32 [n_layers, rows, cols]."""
+        if out is None:
+            out = np.empty((n_layers, *shape), dtype=np.float32)
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.size == n_layers * shape[0] * shape[1]
+        rc = self.lib.sf3d_ext_get_layer_rasters(int(field), first_layer, n_layers, nodata, _ptr(out, C.c_float))
         if rc:
-            raise RuntimeError(f"sf3d_ext_get_layer_raster -> {SF3Derror(rc).name}")
+            raise RuntimeError(f"sf3d_ext_get_layer_rasters -> {SF3Derror(rc).name}")
         return out
 
     def set_fixed_temperature(self, first: int, temperature: np.ndarray, depth: float) -> int:

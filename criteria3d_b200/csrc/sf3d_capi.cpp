@@ -1141,13 +1141,13 @@ uint8_t sf3d_ext_set_forcing_rasters(const sf3d_forcing_desc *f)
     }, (uint8_t)SF3D_MEMORY_ERROR);
 }
 
-uint8_t sf3d_ext_get_layer_raster(int field, uint32_t layer, float nodata, float *dst)
+uint8_t sf3d_ext_get_layer_rasters(int field, uint32_t firstLayer, uint32_t nLayers, float nodata, float *dst)
 {
     return guarded([&]() -> uint8_t {
         REQUIRE_INIT_E();
         if (!dst) return SF3D_PARAMETER_ERROR;
         if (!S.rasterRank) return SF3D_MISSING_DATA_ERROR;
-        if (layer >= S.raster.layers) return SF3D_INDEX_ERROR;
+        if ((uint64_t)firstLayer + nLayers > S.raster.layers || nLayers == 0) return SF3D_INDEX_ERROR;
         switch (field)
         {
             case SF3D_F_WATER_CONTENT: case SF3D_F_DEGREE_OF_SATURATION: case SF3D_F_WATER_CONDUCTIVITY:
@@ -1160,9 +1160,9 @@ uint8_t sf3d_ext_get_layer_raster(int field, uint32_t layer, float nodata, float
         uint8_t rc = sync_to_device();
         if (rc) return rc;
         const size_t cells = (size_t)S.raster.rows * S.raster.cols;
-        float *stage = (float *)raster_stage(cells * sizeof(float));
-        k_layer_raster(S.eng.v, S.raster, field, layer, nodata, stage);
-        d2h(dst, stage, cells * sizeof(float));
+        float *stage = (float *)raster_stage(cells * nLayers * sizeof(float));
+        for (uint32_t l = 0; l < nLayers; ++l) k_layer_raster(S.eng.v, S.raster, field, firstLayer + l, nodata, stage + (size_t)l * cells);
+        d2h(dst, stage, cells * nLayers * sizeof(float));
         return SF3D_OK;
     }, (uint8_t)SF3D_MEMORY_ERROR);
 }

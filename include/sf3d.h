@@ -253,11 +253,13 @@ typedef struct sf3d_forcing_desc {
 } sf3d_forcing_desc;
 uint8_t sf3d_ext_set_forcing_rasters(const sf3d_forcing_desc *desc);
 
-/* sf3d_ext_get_layer_raster: Project3D::computeCriteria3DMap (project3D.cpp:1896-1947) for one layer:
- * dst[cell] = (float) field value of node(layer, cell); nodata for cells outside the catchment and for
- * values equal to -9999; SF3D_F_WATER_CONTENT on layer 0 is converted from [m] to [mm] (:1936-1940).
- * dst is a HOST buffer of rows*cols floats. */
-uint8_t sf3d_ext_get_layer_raster(int field, uint32_t layer, float nodata, float *dst);
+/* sf3d_ext_get_layer_rasters: Project3D::computeCriteria3DMap (project3D.cpp:1896-1947) for layers
+ * [first_layer, first_layer + n_layers), e.g. all layers of the water potential as saveModelsState
+ * writes them (bin/CRITERIA3D/criteria3DProject.cpp:2275-2301):
+ * dst[l][cell] = (float) field value of node(first_layer + l, cell); nodata for cells outside the
+ * catchment and for values equal to -9999; SF3D_F_WATER_CONTENT on layer 0 is converted from [m] to
+ * [mm] (:1936-1940).  dst is a HOST buffer of n_layers*rows*cols floats. */
+uint8_t sf3d_ext_get_layer_rasters(int field, uint32_t first_layer, uint32_t n_layers, float nodata, float *dst);
 
 /* setNodeBoundaryFixedTemperature(i, T[k], depth) for nodes [first, first+count) */
 uint8_t sf3d_ext_set_fixed_temperature(uint32_t first, uint32_t count, const double *temperature, double depth);

@@ -207,7 +207,8 @@ def raster_forcing_and_maps(sf, threads=1):
     shape = (cat.rows, cat.cols)
     out["rasters"] = np.stack([sf.get_layer_raster(Field.WATER_CONTENT, 0, shape), sf.get_layer_raster(Field.WATER_CONTENT, 2, shape),
                                sf.get_layer_raster(Field.DEGREE_OF_SATURATION, 1, shape), sf.get_layer_raster(Field.TOTAL_POTENTIAL, 4, shape),
-                               sf.get_layer_raster(Field.MATRIC_POTENTIAL, 3, shape)])
+                               sf.get_layer_raster(Field.MATRIC_POTENTIAL, 3, shape),
+                               *sf.get_layer_rasters(Field.MATRIC_POTENTIAL, 0, cat.layers, shape)])      # saveModelsState
     return out
 
 

@@ -42,10 +42,12 @@ def contract_codes(sf):
             sf.set_forcing_rasters(precipitation=np.zeros((cat.rows, cat.cols), np.float32)), sf.lib.sf3d_ext_set_forcing_rasters(None)]
     buf = np.zeros((cat.rows, cat.cols), np.float32)
     P = buf.ctypes.data_as(C.POINTER(C.c_float))
-    out += [sf.lib.sf3d_ext_get_layer_raster(int(Field.WATER_CONTENT), cat.layers, -9999.0, P),
-            sf.lib.sf3d_ext_get_layer_raster(int(Field.WATER_SINK_SOURCE), 0, -9999.0, P),
-            sf.lib.sf3d_ext_get_layer_raster(int(Field.WATER_CONTENT), 0, -9999.0, None),
-            sf.lib.sf3d_ext_get_layer_raster(int(Field.WATER_CONTENT), 0, -9999.0, P)]
+    out += [sf.lib.sf3d_ext_get_layer_rasters(int(Field.WATER_CONTENT), cat.layers, 1, -9999.0, P),
+            sf.lib.sf3d_ext_get_layer_rasters(int(Field.WATER_CONTENT), cat.layers - 1, 2, -9999.0, P),
+            sf.lib.sf3d_ext_get_layer_rasters(int(Field.WATER_CONTENT), 0, 0, -9999.0, P),
+            sf.lib.sf3d_ext_get_layer_rasters(int(Field.WATER_SINK_SOURCE), 0, 1, -9999.0, P),
+            sf.lib.sf3d_ext_get_layer_rasters(int(Field.WATER_CONTENT), 0, 1, -9999.0, None),
+            sf.lib.sf3d_ext_get_layer_rasters(int(Field.WATER_CONTENT), 0, 1, -9999.0, P)]
     return np.array(out, dtype=np.float64)
 
 
