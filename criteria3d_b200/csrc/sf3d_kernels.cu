@@ -464,10 +464,10 @@ struct Mbox { double val[2][SF3D_MAX_RANKS][4]; unsigned long long seq[2][SF3D_M
 // lane 0 folds the contributions in rank order, so every rank obtains the bit-identical result.  Two slots
 // by sequence parity: a rank can run at most one call ahead of its slowest peer.  The wait is bounded
 // (about 10 s of SM clocks); on expiry the error flag makes the host abort instead of hanging the GPU.
-__global__ void kern_p2p_allreduce(Mbox *mine, Mbox *const *peers, int rank, int world, unsigned long long seq,
-                                   int count, int isMax, double *values, Ctrl *ctrl)
+__device__ __forceinline__ void p2p_allreduce_warp(Mbox *mine, Mbox *const *peers, int rank, int world, unsigned long long seq,
+                                                   int count, int isMax, double *values, Ctrl *ctrl)
 {
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31;
     const int par = (int)(seq & 1ull);
     if (lane < world)
     {
@@ -494,6 +494,49 @@ __global__ void kern_p2p_allreduce(Mbox *mine, Mbox *const *peers, int rank, int
             values[k] = acc;
         }
         if (mine->error && ctrl) ctrl->status = SOLVE_DIVERGED;
+    }
+}
+__global__ void kern_p2p_allreduce(Mbox *mine, Mbox *const *peers, int rank, int world, unsigned long long seq,
+                                   int count, int isMax, double *values, Ctrl *ctrl)
+{
+    p2p_allreduce_warp(mine, peers, rank, world, seq, count, isMax, values, ctrl);
+}
+
+// One kernel per sweep for everything that follows the Jacobi rows on several GPUs: the boundary rows of x
+// go straight into the neighbours' ghost rows (NVLink peer stores); the block that finishes last then
+// all-reduces the residual sum through the mailboxes -- its system-scope fence orders every block's halo
+// stores before the sequence number the peers wait for -- and applies the stopping rule
+// (cpusolver.cpp:678-700).  Replaces kern_push x peers + kern_p2p_allreduce + kern_rule_jacobi.
+#define SF3D_MAX_HALO_PEERS 4
+struct ExchangeDev {
+    int nPeers;
+    uint32_t nSend[SF3D_MAX_HALO_PEERS];
+    const uint32_t *sendIdx[SF3D_MAX_HALO_PEERS];
+    const uint32_t *remoteIdx[SF3D_MAX_HALO_PEERS];
+    double *peerX[SF3D_MAX_HALO_PEERS];
+};
+__global__ void __launch_bounds__(SF3D_BLOCK) kern_sweep_exchange(const double *__restrict__ x, ExchangeDev e, Mbox *mine, Mbox *const *peers,
+                                                                  int rank, int world, unsigned long long seq, Ctrl *ctrl,
+                                                                  double nGlobal, int maxIter, double tol)
+{
+    if (ctrl->status != SOLVE_RUNNING) return;          // same decision on every rank: the status derives from all-reduced values
+    for (int p = 0; p < e.nPeers; ++p)
+    {
+        const uint32_t *__restrict__ idx = e.sendIdx[p];
+        const uint32_t *__restrict__ rem = e.remoteIdx[p];
+        double *__restrict__ dst = e.peerX[p];
+        for (uint32_t k = blockIdx.x * SF3D_BLOCK + threadIdx.x; k < e.nSend[p]; k += gridDim.x * SF3D_BLOCK) dst[rem[k]] = x[idx[k]];
+    }
+    __threadfence_system();
+    if (!last_block(ctrl)) return;
+    if (threadIdx.x < 32)
+    {
+        p2p_allreduce_warp(mine, peers, rank, world, seq, 1, 0, ctrl->red, ctrl);
+        if (threadIdx.x == 0)
+        {
+            if (ctrl->status == SOLVE_RUNNING) rule_jacobi(ctrl, ctrl->red[0], nGlobal, maxIter, tol);
+            ctrl->ticket = 0;
+        }
     }
 }
 
@@ -1076,6 +1119,28 @@ void comm_allreduce(double *devValues, int count, bool isMax, Ctrl *ctrl)
     }
     NCCL_OK(nccl.AllReduce(devValues, devValues, (size_t)count, NCCL_FLOAT64, isMax ? NCCL_MAX : NCCL_SUM, g_comm, g_stream));
 }
+// direct halo + direct reduce + at most SF3D_MAX_HALO_PEERS neighbours: the fused exchange kernel
+bool comm_sweep_exchange(double *x, Ctrl *ctrl, double nGlobal, int maxIter, double tol)
+{
+    static const bool disabled = getenv("SF3D_FUSED_EXCHANGE") && atoi(getenv("SF3D_FUSED_EXCHANGE")) == 0;
+    if (disabled || g_world <= 1 || !g_directHalo || !g_directReduce || g_halo.size() > SF3D_MAX_HALO_PEERS) return false;
+    const int b = (x == g_localX[1]) ? 1 : 0;
+    ExchangeDev e{};
+    uint32_t most = 1;
+    for (HaloPeer &h : g_halo)
+    {
+        if (!h.nSend) continue;
+        const int p = e.nPeers++;
+        e.nSend[p] = h.nSend; e.sendIdx[p] = h.sendIdx; e.remoteIdx[p] = h.remoteIdx; e.peerX[p] = h.peerX[b];
+        most = h.nSend > most ? h.nSend : most;
+    }
+    int blocks = reduce_blocks(most);
+    if (blocks > 148) blocks = 148;
+    ++g_seq;
+    kern_sweep_exchange<<<blocks, SF3D_BLOCK, 0, g_stream>>>(x, e, g_mbox, g_peerMboxDev, g_rank, g_world, g_seq, ctrl, nGlobal, maxIter, tol);
+    LAUNCH_CHECK();
+    return true;
+}
 void comm_halo(double *x, const Ctrl *ctrl)
 {
     if (g_world <= 1 || g_halo.empty()) return;
@@ -1176,6 +1241,7 @@ void k_jacobi(const SF3DView &v, const double *xin, double *xout, int maxIter, d
     if (v.world > 1)
     {
         ProfScope ps(SF3D_K_COMM);
+        if (comm_sweep_exchange(xout, v.ctrl, v.nGlobal, maxIter, tol)) return;      // one fused kernel over peer memory
         comm_halo(xout, v.ctrl);                         // boundary rows of x -> neighbours' ghost rows
         comm_allreduce(v.ctrl->red, 1, false, v.ctrl);           // residual sum over ranks
         kern_rule_jacobi<<<1, 1, 0, g_stream>>>(v.ctrl, v.nGlobal, maxIter, tol); LAUNCH_CHECK();
