@@ -329,7 +329,10 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_verify_patterns(SF3DView v, c
     }
 }
 
-__global__ void __launch_bounds__(SF3D_BLOCK) kern_begin_try(SF3DView v)
+#ifndef SF3D_POST_BLOCKS
+#define SF3D_POST_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(SF3D_BLOCK, SF3D_POST_BLOCKS) kern_begin_try(SF3DView v)
 {
     for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
         sf3d_row_begin_try(v, i);
@@ -556,7 +559,7 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_unpack(double *__restrict__ x
 }
 
 // H = x, Se refresh, and the two mass-balance sums
-__global__ void __launch_bounds__(SF3D_BLOCK) kern_post(SF3DView v, const double *__restrict__ x, double dt, int mode)
+__global__ void __launch_bounds__(SF3D_BLOCK, SF3D_POST_BLOCKS) kern_post(SF3DView v, const double *__restrict__ x, double dt, int mode)
 {
     __shared__ double sh[SF3D_BLOCK / 32];
     double storage = 0., sinkSum = 0.;
@@ -772,23 +775,26 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_build_grid(SF3DView v, GridDe
 // ------------------------------------------------------------------------------------------
 // coupled heat (Heat::*, CPUSolver::heatLoop)
 // ------------------------------------------------------------------------------------------
+#ifndef SF3D_HEAT_BLOCKS
+#define SF3D_HEAT_BLOCKS 8          // same finding for the heat rows (profiles/r01_occupancy_ab.json)
+#endif
 __global__ void __launch_bounds__(SF3D_BLOCK) kern_update_conductance(SF3DView v)
 {
     for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
         sf3d_row_update_conductance(v, i);
 }
-__global__ void __launch_bounds__(SF3D_BLOCK) kern_heat_coeffs(SF3DView v, double dtHeat, double dtWater)
+__global__ void __launch_bounds__(SF3D_BLOCK, SF3D_HEAT_BLOCKS) kern_heat_coeffs(SF3DView v, double dtHeat, double dtWater)
 {
     for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
         sf3d_row_heat_coeffs(v, i, dtHeat, dtWater);
 }
-__global__ void __launch_bounds__(SF3D_BLOCK) kern_save_water_fluxes(SF3DView v, double dtHeat, double dtWater)
+__global__ void __launch_bounds__(SF3D_BLOCK, SF3D_HEAT_BLOCKS) kern_save_water_fluxes(SF3DView v, double dtHeat, double dtWater)
 {
     for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
         sf3d_row_save_water_fluxes(v, i, dtHeat, dtWater);
 }
 // updateBoundaryHeatData: heat flux per node + max heat-boundary Courant (heat.cpp:237-340)
-__global__ void __launch_bounds__(SF3D_BLOCK) kern_boundary_heat(SF3DView v, double maxTimeStep)
+__global__ void __launch_bounds__(SF3D_BLOCK, SF3D_HEAT_BLOCKS) kern_boundary_heat(SF3DView v, double maxTimeStep)
 {
     __shared__ double sh[SF3D_BLOCK / 32];
     double courant = 0.;
@@ -806,7 +812,7 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_boundary_heat(SF3DView v, dou
     }
 }
 __global__ void kern_rule_heat_courant(Ctrl *c) { c->heatCourantMax = c->red[0]; }
-__global__ void __launch_bounds__(SF3D_BLOCK) kern_heat_begin(SF3DView v, double dtHeat, double dtWater)
+__global__ void __launch_bounds__(SF3D_BLOCK, SF3D_HEAT_BLOCKS) kern_heat_begin(SF3DView v, double dtHeat, double dtWater)
 {
     const size_t N = v.N;
     for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
@@ -820,7 +826,7 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_heat_begin(SF3DView v, double
     if (blockIdx.x == 0 && threadIdx.x == 0)
     { Ctrl *c = v.ctrl; c->status = SOLVE_RUNNING; c->sweeps = 0; c->lastNorm = 0.; }
 }
-__global__ void __launch_bounds__(SF3D_BLOCK) kern_heat_assemble(SF3DView v, double dtHeat, double dtWater)
+__global__ void __launch_bounds__(SF3D_BLOCK, SF3D_HEAT_BLOCKS) kern_heat_assemble(SF3DView v, double dtHeat, double dtWater)
 {
     for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
         if (!(v.world > 1 && META_GHOST(v.meta[i]))) sf3d_row_heat_assemble(v, i, dtHeat, dtWater);
@@ -862,7 +868,7 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_heat_jacobi(SF3DView v, const
         }
     }
 }
-__global__ void __launch_bounds__(SF3D_BLOCK) kern_heat_post(SF3DView v, const double *__restrict__ x, double dtHeat,
+__global__ void __launch_bounds__(SF3D_BLOCK, SF3D_HEAT_BLOCKS) kern_heat_post(SF3DView v, const double *__restrict__ x, double dtHeat,
                                                              double dtWater, int mode)
 {
     __shared__ double sh[SF3D_BLOCK / 32];
@@ -890,7 +896,7 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_heat_post(SF3DView v, const d
     }
 }
 __global__ void kern_rule_heat_post(Ctrl *c) { c->heatStorage = c->red[0]; c->heatSinkSum = c->red[1]; }
-__global__ void __launch_bounds__(SF3D_BLOCK) kern_heat_accept(SF3DView v, double dtHeat, double dtWater)
+__global__ void __launch_bounds__(SF3D_BLOCK, SF3D_HEAT_BLOCKS) kern_heat_accept(SF3DView v, double dtHeat, double dtWater)
 {
     for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
         if (!(v.world > 1 && META_GHOST(v.meta[i]))) sf3d_row_heat_accept(v, i, dtHeat, dtWater);
