@@ -144,6 +144,14 @@ def cpu_run(sample: dict, steps: int, warmup: int, budget_s: float):
     }
 
 
+def config_name(args, world) -> str:
+    """BASELINE.json configuration the shape corresponds to (C2 is the headline single-GPU workload)"""
+    shape = (args.rows * world, args.cols, args.soil_layers)
+    if args.heat and shape == (1024, 1024, 10):
+        return "C3"
+    return {(1024, 1024, 10): "C2", (4096, 4096, 20): "C4", (8192, 8192, 20): "C5"}.get(shape, "C2-like slab" if world > 1 else "custom")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -312,12 +320,15 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": f"C2 synthetic {args.rows}x{args.cols} DEM x (1+{args.soil_layers}) layers, "
+                "workload": f"{config_name(args, world)} synthetic {args.rows}x{args.cols} DEM per GPU x (1+{args.soil_layers}) layers, "
                             f"{RAIN_MM_H:g} mm/h storm hour, " + ("coupled heat (diffusive + latent)" if args.heat else "water only") + ", Richards + Manning runoff",
                 "nodes_per_gpu": N, "links_per_gpu": int(links),
                 "parallelism": "single GPU" if world == 1 else
-                               f"{world} row slabs of {args.rows} DEM rows each (+1 ghost row per side), NCCL halo of x per sweep "
-                               f"+ all-reduce of residual/Courant/balance sums; global catchment {args.rows * world}x{args.cols}",
+                               f"{world} row slabs of {args.rows} DEM rows each (+1 ghost row per side); per sweep: "
+                               + ("boundary rows stored into the neighbours' ghost rows over NVLink peer memory + mailbox all-reduce of the "
+                                  "residual + stopping rule, one fused kernel" if getattr(sf, "halo_mode", "nccl") == "peer-memory"
+                                  else "ncclSend/ncclRecv halo of x + ncclAllReduce of the residual")
+                               + f"; all-reduce of Courant / balance sums per approximation; global catchment {args.rows * world}x{args.cols}",
                 "l2": "working set per sweep (12 B/link + 32 B/node = %.2f GB) >> 126 MB L2; no explicit flush" % (bytes_sweep / 1e9),
                 "numerics": "setNumericalParameters(0.5, 3600, 150, 10, 10, 3)",
             },

@@ -44,6 +44,9 @@ def setup_slab(sf: SoilFluxes3D, rows: int, cols: int, n_soil_layers: int, rank:
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             if int(flag.item()) == 0:
                 _ok(sf.set_halo(peers, send, recv, slab.n_global), "sf3d_ext_set_halo")      # drops every IPC mapping
+            sf.halo_mode = "peer-memory" if int(flag.item()) else "nccl"
+        else:
+            sf.halo_mode = "nccl"
         _ok(sf.initializeBalance(), "initializeBalance")
     return slab, cat
 
