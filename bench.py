@@ -312,7 +312,9 @@ def main():
         tfile = ROOT / "profiles" / "jacobi_traffic.json"
         if tfile.exists():
             try:
-                traffic = json.loads(tfile.read_text()).get("dram_bytes_per_launch")
+                tj = json.loads(tfile.read_text())
+                # the capture is of the C2 single-GPU shape; other shapes have no capture
+                traffic = tj.get("dram_bytes_per_launch") if int(tj.get("nodes", 0)) == int(N) else None
             except Exception:
                 traffic = None
         line = {
@@ -347,8 +349,9 @@ def main():
                          "bytes_per_launch": bytes_sweep, "avg_launch_ms": jac["ms"] / max(sweeps, 1),
                          "launches": jac["launches"], "executed_sweeps": int(sweeps),
                          "frac_of_nominal_8000": (jac_gbs / 8000.0) if jac_gbs else None,
+                         "frac_traffic": (traffic / (jac["ms"] / max(sweeps, 1) * 1e-3) / 1e9 / peak) if (traffic and jac["ms"] > 0) else None,
                          "note": "achieved counts ALGORITHMIC bytes; the kernel moves fewer (traffic) because column "
-                                 "indices are pattern-compressed, so frac can exceed 1"},
+                                 "indices are pattern-compressed, so frac can exceed 1; frac_traffic = measured DRAM bytes (ncu) / time / peak"},
             "roofline_assembly": {"kernel": "kern_node_phase + kern_assemble", "bound": "fp64 issue (HBM reported)",
                                   "achieved": asm_gbs, "peak": peak, "unit": "GB/s", "frac": (asm_gbs / peak) if asm_gbs else None,
                                   "bytes_per_approximation": bytes_asm, "avg_ms_per_approximation": asm_ms / max(approx, 1)},
