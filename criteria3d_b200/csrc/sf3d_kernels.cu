@@ -428,7 +428,10 @@ __global__ void __launch_bounds__(SF3D_BLOCK, HEAT ? SF3D_HEAT_ASSEMBLE_BLOCKS :
 
 // one Jacobi sweep (Water::JacobiWaterCPU) + the stopping rule of CPUSolver::solveLinearSystem
 // (cpusolver.cpp:678-700) evaluated by the last block.  Ghost rows are filled by the halo exchange.
-__global__ void __launch_bounds__(SF3D_BLOCK) kern_jacobi(SF3DView v, const double *__restrict__ xin,
+#ifndef SF3D_JACOBI_BLOCKS
+#define SF3D_JACOBI_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(SF3D_BLOCK, SF3D_JACOBI_BLOCKS) kern_jacobi(SF3DView v, const double *__restrict__ xin,
                                                           double *__restrict__ xout, int maxIter, double tol)
 {
     if (v.ctrl->status != SOLVE_RUNNING) return;
