@@ -75,7 +75,7 @@ struct State {
     // device-only
     double *bestH = nullptr, *SeOld = nullptr, *wFlow = nullptr, *lgeom = nullptr, *mval = nullptr,
            *b = nullptr, *cap = nullptr, *x0 = nullptr, *x1 = nullptr, *partA = nullptr, *partB = nullptr,
-           *partC = nullptr, *scratch = nullptr;
+           *scratch = nullptr;
     uint32_t *mcol = nullptr;
     uint16_t *pid = nullptr; int32_t *pattern = nullptr; bool patternsOk = false;
     uint32_t hotPid = 0; int32_t hotOff[SF3D_NLINK] = {0};
@@ -123,13 +123,13 @@ void fill_view()
     v.bSlope = S.bSlope.d; v.bSize = S.bSize.d; v.bRate = S.bRate.d; v.bSum = S.bSum.d; v.bPresc = S.bPresc.d;
     v.lidx = S.lidx.d; v.larea = S.larea.d; v.lflow = S.lflow.d; v.lgeom = S.lgeom;
     v.H = S.H.d; v.oldH = S.oldH.d; v.bestH = S.bestH; v.Se = S.Se.d; v.SeOld = S.SeOld; v.K = S.K.d;
-    v.wFlow = S.wFlow; v.sink = S.sink.d; v.pond = S.pond.d; v.inv = nullptr;
+    v.wFlow = S.wFlow; v.sink = S.sink.d; v.pond = S.pond.d;
     v.mcol = S.mcol; v.pid = S.patternsOk ? S.pid : nullptr; v.pattern = S.patternsOk ? S.pattern : nullptr; v.mval = S.mval;
     v.hotPid = S.hotPid; memcpy(v.hotOff, S.hotOff, sizeof v.hotOff); v.b = S.b; v.cap = S.cap; v.x0 = S.x0; v.x1 = S.x1;
     v.soil = S.dSoil; v.rough = S.dRough;
     v.culverts = S.culverts.empty() ? nullptr : S.dCulv;
     v.culvertOf = S.culverts.empty() ? nullptr : S.culvertOf.d;
-    v.ctrl = S.ctrl; v.partA = S.partA; v.partB = S.partB; v.partC = S.partC;
+    v.ctrl = S.ctrl; v.partA = S.partA; v.partB = S.partB;
     if (S.heat)
     {
         v.T = S.T.d; v.oldT = S.oldT.d; v.hFlux = S.hFlux; v.hSink = S.hSink.d;
@@ -273,7 +273,7 @@ void release_all()
     { double **hd[] = {&S.hFlux, &S.lwFlux, &S.lvFlux, &S.hdiag, &S.hTVK, &S.hIVK, &S.hCond, &S.hTm, &S.hTLK, &S.hTLKh, &S.hPress, &S.ldist3}; for (double **p : hd) { dev_free(*p); *p = nullptr; } }
     S.hfTypesAllocated = 0;
     double **devOnly[] = {&S.bestH, &S.SeOld, &S.wFlow, &S.lgeom, &S.mval, &S.b, &S.cap, &S.x0, &S.x1,
-                          &S.partA, &S.partB, &S.partC, &S.scratch};
+                          &S.partA, &S.partB, &S.scratch};
     for (double **p : devOnly) { dev_free(*p); *p = nullptr; }
     dev_free(S.mcol); S.mcol = nullptr;
     dev_free(S.pid); S.pid = nullptr; dev_free(S.pattern); S.pattern = nullptr; S.patternsOk = false;
@@ -329,7 +329,7 @@ uint8_t sf3d_initialize(uint32_t nrNodes, uint32_t nrSurfaceNodes, uint8_t nrLat
         S.b = (double *)dev_alloc(N * 8); S.cap = (double *)dev_alloc(N * 8);
         S.x0 = (double *)dev_alloc(N * 8); S.x1 = (double *)dev_alloc(N * 8);
         const size_t nb = (size_t)std::max(reduce_blocks(0xFFFFFFFFu), wide_blocks(0xFFFFFFFFu));
-        S.partA = (double *)dev_alloc(nb * 8); S.partB = (double *)dev_alloc(nb * 8); S.partC = (double *)dev_alloc(nb * 8);
+        S.partA = (double *)dev_alloc(nb * 8); S.partB = (double *)dev_alloc(nb * 8);
         S.ctrl = (Ctrl *)dev_alloc(sizeof(Ctrl));
         if (S.heat)
         {

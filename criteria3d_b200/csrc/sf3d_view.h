@@ -107,7 +107,7 @@ struct SF3DView {
     double *larea, *lflow;
     double *lgeom;                  // static link geometry, COLUMN-major (see sf3d_link_geom)
     // water state
-    double *H, *oldH, *bestH, *Se, *SeOld, *K, *wFlow, *sink, *pond, *inv;
+    double *H, *oldH, *bestH, *Se, *SeOld, *K, *wFlow, *sink, *pond;
     // linear system, COLUMN-major: [col*N + i]; mcol is static
     uint32_t *mcol;
     // pattern-compressed column indices: mcol[c][i] == i + pattern[pid[i]*10 + c] for every node
@@ -140,5 +140,5 @@ struct SF3DView {
     double *ldist3;                 // static: nodeDistance3D per link, slot-major (soilPhysics.cpp:331-335)
     // control / reduction scratch
     Ctrl *ctrl;
-    double *partA, *partB, *partC;  // per-block partials
+    double *partA, *partB;          // per-block partials
 };
