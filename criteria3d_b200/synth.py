@@ -57,27 +57,16 @@ def _hash01(seed: int, a: np.ndarray, b: np.ndarray) -> np.ndarray:
 
 
 def _raster_slope_and_outlet(dem: np.ndarray, valid: np.ndarray, cell: float):
-    """Harness-side stand-in for gis::computeSlopeAspectMaps / gis::isBoundaryRunoff (agrolib/gis, out of
-    scope): slope = gradient magnitude over valid neighbours; outlet = valid cells on the
-    catchment rim (next to NODATA or the raster edge) lying below the mean of their valid neighbours."""
-    R, C = dem.shape
-    z = np.where(valid, dem.astype(np.float64), np.nan)
-    zp = np.pad(z, 1, constant_values=np.nan)
-    nb = np.stack([zp[1 + di: 1 + di + R, 1 + dj: 1 + dj + C] for di in (-1, 0, 1) for dj in (-1, 0, 1) if (di, dj) != (0, 0)])
-    def diff(a, b):
-        d = (a - b) / (2 * cell)
-        one = np.where(np.isnan(a), (z - b) / cell, (a - z) / cell)
-        return np.where(np.isnan(a) | np.isnan(b), np.where(np.isnan(one), 0.0, one), d)
-    gx = diff(zp[1:-1, 2:], zp[1:-1, :-2])
-    gy = diff(zp[2:, 1:-1], zp[:-2, 1:-1])
-    slope = np.where(valid, np.sqrt(gx * gx + gy * gy), 0.0)
-    rim = valid & np.isnan(nb).any(axis=0)
-    import warnings
-    with np.errstate(invalid="ignore"), warnings.catch_warnings():
-        warnings.simplefilter("ignore", RuntimeWarning)
-        lower = z < np.nanmean(nb, axis=0)
-    outlet = (rim & lower).astype(np.uint8)
-    return np.ascontiguousarray(slope, dtype=np.float32), np.ascontiguousarray(outlet)
+    """Slope and runoff boundary of a real raster exactly as the reference's caller prepares them:
+    gis::computeSlopeAspectMaps, Project3D::setLateralBoundary (gis::isBoundaryRunoff) and the
+    tan(slope) of Project3D::setCrit3DTopography, restated in criteria3d_b200/raster.py and pinned bit for bit
+    against the reference's own gis code (tests/test_raster.py)."""
+    from .raster import boundary_runoff, boundary_slope_tan, slope_aspect
+    nodata = -9999.0
+    z = np.where(valid, dem, np.float32(nodata)).astype(np.float32)
+    slope_deg, aspect = slope_aspect(z, cell, nodata)
+    tan = np.where(valid, boundary_slope_tan(slope_deg), np.float32(0.0)).astype(np.float32)
+    return np.ascontiguousarray(tan), np.ascontiguousarray(boundary_runoff(z, aspect, nodata))
 
 
 def soil_layers(n_soil_layers: int, min_t=0.02, max_t=0.10, max_t_depth=0.40):

@@ -57,8 +57,34 @@ def jacobi_kat(ref):
     print("jacobi_kat: 2 systems of", n, "rows")
 
 
+def gis_reference(dem, cell, flag=-9999.0):
+    """slope [deg], aspect [deg], runoff boundary mask and tan(slope) from the reference's own gis code
+    (oracle/_ref/libgis_ref.so = agrolib/gis compiled where it lies + oracle/gis_ref_capi.cpp)"""
+    import ctypes as C
+    lib = C.CDLL(str(ROOT / "oracle" / "_ref" / "libgis_ref.so"))
+    d = np.ascontiguousarray(dem, np.float32)
+    rows, cols = d.shape
+    slope, aspect, tan = np.empty_like(d), np.empty_like(d), np.empty_like(d)
+    boundary = np.empty(d.shape, np.uint8)
+    P = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+    rc = lib.gisref_slope_aspect_boundary(rows, cols, C.c_double(cell), C.c_float(flag), P(d, C.c_float), P(slope, C.c_float),
+                                          P(aspect, C.c_float), P(boundary, C.c_uint8), P(tan, C.c_float))
+    assert rc == 0
+    return slope, aspect, boundary, tan
+
+
+def gis_golden():
+    """the reference's slope / aspect / runoff boundary of the bundled STH DEM -> tests/golden/gis_sth.npz"""
+    with np.load(Path(__file__).parent / "config1_sth_inputs.npz") as z:
+        dem, cell = z["dem"], float(z["cell"])
+    slope, aspect, boundary, tan = gis_reference(dem, cell)
+    np.savez_compressed(Path(__file__).parent / "gis_sth.npz", slope=slope, aspect=aspect, boundary=boundary, tan=tan)
+    print("gis_sth:", int(boundary.sum()), "runoff boundary cells")
+
+
 def main():
     config1_inputs()
+    gis_golden()
     jacobi_kat(SoilFluxes3D(REFERENCE_LIB))
     ref = SoilFluxes3D(REFERENCE_LIB)
     assert ref.backend == "reference"

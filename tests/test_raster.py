@@ -1,5 +1,8 @@
 """ESRI float grid I/O of the harness (the format of the reference's DEMs, soil maps and saved states)."""
+from pathlib import Path
+
 import numpy as np
+import pytest
 
 from criteria3d_b200.raster import EsriGrid, layer_to_grid, read_flt, write_flt
 from criteria3d_b200.synth import Catchment
@@ -23,3 +26,64 @@ def test_layer_to_grid_places_values_by_cell_rank():
     g = layer_to_grid(layer, cat.cell_rank, like)
     assert np.array_equal(g.values, np.array([[10, -9999, 11], [12, 13, -9999]], np.float32))
     assert cat.n_surface == 4 and cat.rain_sink_source(3.6).shape == (4,)
+
+
+# ---- slope / aspect / runoff boundary: numpy restatement vs the reference's own gis code -------------
+GOLDEN = Path(__file__).parent / "golden"
+GIS_REF = Path(__file__).resolve().parent.parent / "oracle" / "_ref" / "libgis_ref.so"
+
+
+def _ours(dem, cell):
+    from criteria3d_b200.raster import boundary_runoff, boundary_slope_tan, slope_aspect
+    slope, aspect = slope_aspect(dem, cell)
+    return slope, aspect, boundary_runoff(dem, aspect), boundary_slope_tan(slope)
+
+
+def test_slope_aspect_boundary_match_reference_golden():
+    """bundled STH DEM (config 1): bit-identical float maps and boundary mask (golden from the reference's gis.cpp)"""
+    with np.load(GOLDEN / "config1_sth_inputs.npz") as z:
+        dem, cell = z["dem"], float(z["cell"])
+    with np.load(GOLDEN / "gis_sth.npz") as g:
+        slope, aspect, boundary, tan = _ours(dem, cell)
+        valid = dem != np.float32(-9999)
+        assert np.array_equal(slope, g["slope"]) and np.array_equal(aspect, g["aspect"])
+        assert np.array_equal(boundary, g["boundary"]) and int(boundary.sum()) > 0
+        assert np.array_equal(tan[valid], g["tan"][valid])
+
+
+def _cases():
+    rng = np.random.default_rng(11)
+    ragged = (200 + rng.random((61, 47)) * 30).astype(np.float32)
+    ragged[rng.random(ragged.shape) < 0.15] = -9999
+    bowl = (np.hypot(*np.mgrid[-8:9, -10:11]) * 0.7 + 50).astype(np.float32)          # strict minimum in the middle
+    bowl[0:3, 0:4] = -9999
+    return {"ragged": (ragged, 10.0), "flat": (np.full((9, 9), 100, np.float32), 5.0), "bowl": (bowl, 2.0),
+            "one row": ((100 + np.arange(12, dtype=np.float32))[None, :], 4.0), "one cell": (np.full((1, 1), 7, np.float32), 1.0),
+            "all nodata": (np.full((4, 5), -9999, np.float32), 3.0)}
+
+
+@pytest.mark.skipif(not GIS_REF.exists(), reason="oracle/_ref/libgis_ref.so not built (needs /root/reference)")
+@pytest.mark.parametrize("name", sorted(_cases()))
+def test_slope_aspect_boundary_match_reference_library(name):
+    import sys
+    sys.path.insert(0, str(GOLDEN))
+    from make_golden import gis_reference
+    dem, cell = _cases()[name]
+    ours, ref = _ours(dem, cell), gis_reference(dem, cell)
+    valid = dem != np.float32(-9999)
+    for a, b, what in zip(ours[:3], ref[:3], ("slope", "aspect", "boundary")):
+        assert np.array_equal(a, b), what
+    assert np.array_equal(ours[3][valid], ref[3][valid])
+
+
+@pytest.mark.skipif(not (GIS_REF.exists() and Path("/root/reference/DATA/DEM/DEM_Ravone.flt").exists()), reason="reference data absent")
+def test_slope_aspect_boundary_ravone_dem():
+    """the 519 x 1208 Ravone DEM shipped with the reference (422 282 valid cells)"""
+    import sys
+    sys.path.insert(0, str(GOLDEN))
+    from make_golden import gis_reference
+    from criteria3d_b200.raster import read_flt
+    g = read_flt("/root/reference/DATA/DEM/DEM_Ravone.flt")
+    ours, ref = _ours(g.values, g.cell), gis_reference(g.values, g.cell)
+    for a, b in zip(ours[:3], ref[:3]):
+        assert np.array_equal(a, b)
