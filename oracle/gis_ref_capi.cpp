@@ -2,7 +2,7 @@
  * gis_ref_capi.cpp -- TEST INFRASTRUCTURE (oracle side only): the reference's own raster helpers behind a C call.
  *
  * Compiled by oracle/Makefile into oracle/_ref/libgis_ref.so together with the UNMODIFIED reference sources
- * agrolib/gis/{gis,color}.cpp, agrolib/mathFunctions/{basicMath,statistics,furtherMathFunctions,physics}.cpp and
+ * agrolib/gis/{gis,gisIO,color}.cpp, agrolib/mathFunctions/{basicMath,statistics,furtherMathFunctions,physics}.cpp and
  * agrolib/crit3dDate/{crit3dDate,crit3dTime}.cpp (Qt-free), where they lie under /root/reference.  This file
  * only builds the grids and forwards to
  *   gis::computeSlopeAspectMaps      (gis.cpp:1190-1268; boundary cells: computeSlopeAspectBoundary :1114-1186)
@@ -54,4 +54,35 @@ extern "C" int gisref_slope_aspect_boundary(int rows, int cols, double cell, flo
             boundarySlopeTan[k] = boundarySlope;
         }
     return 0;
+}
+
+/* ESRI float grid I/O of the reference (agrolib/gis/gisIO.cpp: readEsriGridFlt :1587, writeEsriGrid :1575),
+ * fileName WITHOUT extension as the reference passes it.  Checker of criteria3d_b200/raster.py read_flt / write_flt. */
+extern "C" int gisref_read_flt(const char *fileNameNoExt, int *rows, int *cols, double *cell, double *xll, double *yll,
+                               float *flag, float *values, long capacity)
+{
+    gis::Crit3DRasterGrid grid;
+    std::string error;
+    if (!gis::readEsriGridFlt(fileNameNoExt, &grid, error)) return 1;
+    *rows = grid.header->nrRows; *cols = grid.header->nrCols; *cell = grid.header->cellSize;
+    *xll = grid.header->llCorner.x; *yll = grid.header->llCorner.y; *flag = grid.header->flag;
+    if ((long)grid.header->nrRows * grid.header->nrCols > capacity) return 2;
+    for (int r = 0; r < grid.header->nrRows; ++r)
+        for (int c = 0; c < grid.header->nrCols; ++c) values[(size_t)r * grid.header->nrCols + c] = grid.value[r][c];
+    return 0;
+}
+
+extern "C" int gisref_write_flt(const char *fileNameNoExt, int rows, int cols, double cell, double xll, double yll,
+                                float flag, const float *values)
+{
+    gis::Crit3DRasterHeader header;
+    header.nrRows = rows; header.nrCols = cols; header.cellSize = cell; header.flag = flag;
+    header.llCorner.x = xll; header.llCorner.y = yll;
+    gis::Crit3DRasterGrid grid;
+    if (!grid.initializeGrid(header)) return 1;
+    for (int r = 0; r < rows; ++r)
+        for (int c = 0; c < cols; ++c) grid.value[r][c] = values[(size_t)r * cols + c];
+    grid.isLoaded = true;
+    std::string error;
+    return gis::writeEsriGrid(fileNameNoExt, &grid, error) ? 0 : 3;
 }

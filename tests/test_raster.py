@@ -87,3 +87,44 @@ def test_slope_aspect_boundary_ravone_dem():
     ours, ref = _ours(g.values, g.cell), gis_reference(g.values, g.cell)
     for a, b in zip(ours[:3], ref[:3]):
         assert np.array_equal(a, b)
+
+
+# ---- ESRI grid I/O against the reference's own reader / writer (agrolib/gis/gisIO.cpp) -------------------------------
+def _ref_read(noext, cap=4_000_000):
+    import ctypes as C
+    lib = C.CDLL(str(GIS_REF))
+    r, c, cell, xll, yll, flag = C.c_int(), C.c_int(), C.c_double(), C.c_double(), C.c_double(), C.c_float()
+    v = np.empty(cap, np.float32)
+    rc = lib.gisref_read_flt(str(noext).encode(), C.byref(r), C.byref(c), C.byref(cell), C.byref(xll), C.byref(yll), C.byref(flag),
+                             v.ctypes.data_as(C.POINTER(C.c_float)), C.c_long(cap))
+    assert rc == 0
+    return v[: r.value * c.value].reshape(r.value, c.value).copy(), (cell.value, xll.value, yll.value, flag.value)
+
+
+@pytest.mark.skipif(not GIS_REF.exists(), reason="oracle/_ref/libgis_ref.so not built (needs /root/reference)")
+def test_flt_files_interchange_with_the_reference_reader_and_writer(tmp_path):
+    import ctypes as C
+    vals = np.arange(35, dtype=np.float32).reshape(5, 7) * 1.25
+    vals[2, 3] = -9999
+    # ours written -> the reference reads the same grid and header
+    write_flt(tmp_path / "ours.flt", EsriGrid(vals, 641947.15, 5724524.79, 2.5, -9999.0))
+    data, hdr = _ref_read(tmp_path / "ours")
+    assert np.array_equal(data, vals) and hdr == (2.5, 641947.15, 5724524.79, -9999.0)
+    # the reference writes -> ours reads; identical payload bytes.  (The reference's header writer prints coordinates with
+    # ofstream's default 6 significant digits, gisIO.cpp:1476-1483; ours keeps them in full.)
+    lib = C.CDLL(str(GIS_REF))
+    rc = lib.gisref_write_flt(str(tmp_path / "theirs").encode(), 5, 7, C.c_double(2.5), C.c_double(641947.15), C.c_double(5724524.79),
+                              C.c_float(-9999), vals.ctypes.data_as(C.POINTER(C.c_float)))
+    assert rc == 0
+    g = read_flt(tmp_path / "theirs.flt")
+    assert np.array_equal(g.values, vals) and g.cell == 2.5 and g.nodata == -9999.0
+    assert (tmp_path / "theirs.flt").read_bytes() == (tmp_path / "ours.flt").read_bytes()
+
+
+@pytest.mark.skipif(not (GIS_REF.exists() and Path("/root/reference/DATA/PROJECT/STH/MAPS/DEM_STH.flt").exists()), reason="reference data absent")
+def test_bundled_dem_reads_like_the_reference_reader():
+    data, hdr = _ref_read("/root/reference/DATA/PROJECT/STH/MAPS/DEM_STH")
+    g = read_flt("/root/reference/DATA/PROJECT/STH/MAPS/DEM_STH.flt")
+    assert np.array_equal(data, g.values) and hdr == (g.cell, g.xll, g.yll, np.float32(g.nodata))
+    with np.load(GOLDEN / "config1_sth_inputs.npz") as z:          # the committed inputs of config 1 are this file
+        assert np.array_equal(z["dem"], g.values)
