@@ -110,7 +110,8 @@ class ClockSampler:
 
 def cpu_run(sample: dict, steps: int, warmup: int, budget_s: float):
     """Time the reference CPU implementation (all host threads) on a bounded sample."""
-    from criteria3d_b200 import ORACLE_LIB, REFERENCE_LIB, Field, SoilFluxes3D
+    from criteria3d_b200 import Field, SoilFluxes3D
+    from oracle import ORACLE_LIB, REFERENCE_LIB
     from criteria3d_b200.synth import Catchment, setup
     if REFERENCE_LIB.exists():
         sf, kind = SoilFluxes3D(REFERENCE_LIB), "reference"

@@ -10,8 +10,9 @@ test code reads like a caller of the reference plugin API:
     dt = sf.computeStep(3600.0)
 
 Three libraries implement the ABI (see include/sf3d.h): the CUDA product, the CPU
-restatement (oracle/) and the unmodified reference (oracle/_ref/).  This module is plumbing
-only; it never chooses an implementation on behalf of the caller and has no fallback.
+restatement and the unmodified reference; the paths of the two checkers live in oracle/__init__.py
+(test infrastructure), not here.  This module is plumbing only; it never chooses an
+implementation on behalf of the caller and has no fallback.
 """
 from __future__ import annotations
 
@@ -24,8 +25,6 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parent.parent
 PRODUCT_LIB = ROOT / "criteria3d_b200" / "libsf3d_b200.so"
-ORACLE_LIB = ROOT / "oracle" / "libsf3d_oracle.so"
-REFERENCE_LIB = ROOT / "oracle" / "_ref" / "libsf3d_ref.so"
 
 
 class SF3Derror(enum.IntEnum):  # types.h:39-40
@@ -157,6 +156,7 @@ class Counters(C.Structure):
         ("kernel_launches", C.c_uint64),
         ("delta_t_curr", C.c_double), ("last_courant", C.c_double),
         ("last_mbr", C.c_double), ("last_mbe", C.c_double), ("links", C.c_uint64),
+        ("heat_cap_hits", C.c_uint64),
     ]
 
     def as_dict(self):

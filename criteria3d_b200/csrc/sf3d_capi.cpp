@@ -530,7 +530,7 @@ uint8_t sf3d_set_culvert(uint32_t nodeIndex, double roughness, double slope, dou
         for (; k < S.culverts.size(); ++k)
             if (S.culverts[k].roughness == roughness && S.culverts[k].width == width && S.culverts[k].height == height) break;
         if (k == S.culverts.size()) { S.culverts.push_back(CulvertRec{width, height, roughness}); S.tablesDirty = true; }
-        S.culvertOf.rw()[nodeIndex] = (uint32_t)k;
+        S.culvertOf.rw()[nodeIndex] = (uint32_t)k + 1u;         // 0 = no culvert record on this node
         return SF3D_OK;
     }, (uint8_t)SF3D_MEMORY_ERROR);
 }

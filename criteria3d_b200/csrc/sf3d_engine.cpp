@@ -125,6 +125,7 @@ bool Engine::heatLoop(double timeStepHeat, double timeStepWater)
         batch = std::min(batch * 2, 64);
     }
     cnt.heat_sweeps += (uint64_t)c.sweeps;
+    if (c.status != SOLVE_CONVERGED) ++cnt.heat_cap_hits;       // stopped at the cap: the result depends on the sweep (Q6)
     const double *x = xbuf(c.sweeps & 1);
 
     k_heat_post(v, x, timeStepHeat, timeStepWater, 0);  // T = x ; heat storage ; heat sink sum

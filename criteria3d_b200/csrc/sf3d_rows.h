@@ -181,6 +181,10 @@ SF3D_HD double sf3d_culvert_flow(double waterLevel, double pond, double width, d
     return flow;
 }
 
+// pond of a node as the reference stores it: per node, NODATA on soil nodes (soilFluxes3D.cpp:616); the device
+// array has surface entries only, so a Runoff type on a soil node must not index it
+SF3D_HD double sf3d_pond(const SF3DView &v, uint32_t i) { return (i < v.Ns) ? v.pond[i] : SF3D_NODATA; }
+
 // HEAT is a compile-time switch so that the water-only kernels carry none of the heat closures
 template <bool HEAT>
 SF3D_HD void sf3d_row_node_phase(const SF3DView &v, uint32_t i, double dt, int withCapacity)
@@ -238,7 +242,7 @@ SF3D_HD void sf3d_row_node_phase(const SF3DView &v, uint32_t i, double dt, int w
         case BT_RUNOFF:
         {
             const double avgH = 0.5 * (H + oldH);
-            const double hs = sf3d_max(0., avgH - (z + v.pond[i]));
+            const double hs = sf3d_max(0., avgH - (z + sf3d_pond(v, i)));
             if (hs < SF3D_EPSILON_RUNOFF) break;
             const double maxFlow = (hs * v.size[i]) / dt;
             const double vel = pow(hs, 2. / 3.) * sqrt(v.bSlope[i]) / v.rough[v.tab[i]];
@@ -273,9 +277,12 @@ SF3D_HD void sf3d_row_node_phase(const SF3DView &v, uint32_t i, double dt, int w
             // Reference water.cpp:749-795 is unreachable (culvertPtr never allocated) and uses
             // 0.5*(H - oldH) - z; the v1 code (old/old_boundary.cpp:377) used the mean head.  The
             // physical (v1) form is built here; see DESIGN.md "deviations".
-            if (v.culverts && v.culvertOf)
+            // a Culvert type set through setNode / setNodeBoundary without setCulvert has no record (the
+            // reference would dereference a null pointer there): no flow
+            const uint32_t rec = (v.culverts && v.culvertOf && i < v.Ns) ? v.culvertOf[i] : 0u;
+            if (rec)
             {
-                const CulvertRec c = v.culverts[v.culvertOf[i]];
+                const CulvertRec c = v.culverts[rec - 1u];
                 const double waterLevel = 0.5 * (H + oldH) - z;
                 rate = -sf3d_culvert_flow(waterLevel, v.pond[i], c.width, c.height, c.roughness, v.bSlope[i], v.bSize[i]);
             }

@@ -122,7 +122,7 @@ struct SF3DView {
     const SoilRec *soil;
     const double *rough;
     const CulvertRec *culverts;     // null when no culvert is defined
-    const uint32_t *culvertOf;      // [Ns] index into culverts
+    const uint32_t *culvertOf;      // [Ns] 1 + index into culverts; 0 = the node has no culvert record
     // heat (null when !computeHeat)
     double *T, *oldT, *hFlux, *hSink;
     double *hbHeightWind, *hbHeightT, *hbRough, *hbAero, *hbSoilCond, *hbT, *hbRH, *hbWind, *hbNetIrr;

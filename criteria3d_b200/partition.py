@@ -88,6 +88,12 @@ class Slab:
 
 
 def make_slab(rows: int, cols: int, n_soil_layers: int, world: int, rank: int) -> Slab:
+    """Row slab of a FULLY VALID rectangular raster (node id = layer * rows * cols + row * cols + col).
+    Rasters with NODATA cells number their nodes by cell rank instead: use partition_graph for those."""
+    if not 0 <= rank < world:
+        raise ValueError(f"rank {rank} outside [0, {world})")
+    if rows < world:
+        raise ValueError(f"{rows} DEM rows cannot be split into {world} non-empty row slabs")
     r0, r1 = slab_rows(rows, world, rank)
     return Slab(rank=rank, world=world, rows=rows, cols=cols, layers=n_soil_layers + 1, r0=r0, r1=r1,
                 top_ghost=1 if rank > 0 else 0, bottom_ghost=1 if rank < world - 1 else 0)
@@ -95,6 +101,9 @@ def make_slab(rows: int, cols: int, n_soil_layers: int, world: int, rank: int) -
 
 def slab_catchment(slab: Slab, **kw) -> Catchment:
     """The local raster of a slab: the same seeded generator evaluated on the slab's global rows."""
+    if kw.get("valid") is not None:
+        raise ValueError("row slabs assume a raster without NODATA cells (the halo lists are computed from "
+                         "row / column arithmetic); partition ragged catchments with partition_graph")
     return Catchment(slab.local_rows, slab.cols, slab.layers - 1, row0=slab.local_row0, global_rows=slab.rows, **kw)
 
 

@@ -236,9 +236,11 @@ class Catchment:
 
 
 def setup(sf: SoilFluxes3D, cat: Catchment, threads: int = 0,
-          numerics: tuple | None = None) -> None:
+          numerics: tuple | None = None, heat_flux_mode: int | None = None) -> None:
     """initialize3DModel's call sequence (project3D.cpp:456-616) on implementation `sf`."""
     hf = HeatFluxSaveMode.Total if cat.heat else HeatFluxSaveMode.None_
+    if heat_flux_mode is not None:
+        hf = HeatFluxSaveMode(heat_flux_mode)
     sf.reset_solver()       # same starting deltaTcurr as a fresh process (see sf3d_ext_reset_solver)
     _ok(sf.initializeSF3D(cat.n_nodes, cat.n_surface, 8, True, cat.heat, False, int(hf)), "initializeSF3D")
     for i, (rough, _pond) in enumerate(SURFACE_TABLE):
@@ -256,19 +258,20 @@ def setup(sf: SoilFluxes3D, cat: Catchment, threads: int = 0,
     sf.setThreadsNumber(threads)
     _ok(sf.set_field(Field.MATRIC_POTENTIAL, 0, cat.initial_matric_potential()), "initial matric potential")
     if cat.heat:
-        setup_heat(sf, cat)
+        setup_heat(sf, cat, mode=int(hf))
     _ok(sf.initializeBalance(), "initializeBalance")
 
 
-def setup_heat(sf: SoilFluxes3D, cat: Catchment, hour: int = 0, advection: bool = False, latent: bool = True) -> None:
+def setup_heat(sf: SoilFluxes3D, cat: Catchment, hour: int = 0, advection: bool = False, latent: bool = True,
+               mode: int = int(HeatFluxSaveMode.Total)) -> None:
     """C3 heat configuration: T0 = 288.15 K; HeatSurface boundary on the first soil layer
     (set by the grid builder) with 2 m measurement heights and 0.01 m roughness; fixed 285.15 K at
     0.3 m below the free-drainage bottom nodes; total heat flux saved; latent heat on.
-    Advection defaults to OFF: with it on, the reference itself returns NaN temperatures from the
-    first heat sub-step on these catchments (verified with oracle/_ref), so
-    there is nothing to be in parity with."""
+    Advection defaults to OFF: with it on, the reference's temperatures run away (SURVEY Appendix B Q1:
+    its advective term is not conservative) and reach NaN within one 600 s water step on these catchments;
+    the advective term is pinned on short bounded steps instead (tests/scenarios.py heat_advective_*)."""
     ns, n = cat.n_surface, cat.n_nodes
-    _ok(sf.initializeHeatFlag(int(HeatFluxSaveMode.Total), advection, latent), "initializeHeatFlag")
+    _ok(sf.initializeHeatFlag(int(mode), advection, latent), "initializeHeatFlag")
     _ok(sf.set_field(Field.TEMPERATURE, ns, np.full(n - ns, 288.15)), "setNodeTemperature")
     for f, val in ((Field.BOUNDARY_HEIGHT_WIND, 2.0), (Field.BOUNDARY_HEIGHT_TEMPERATURE, 2.0), (Field.BOUNDARY_ROUGHNESS, 0.01)):
         _ok(sf.set_field(f, ns, np.full(ns, val)), f.name)

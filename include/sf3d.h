@@ -278,6 +278,9 @@ typedef struct sf3d_counters {
     double   last_mbr;         /* balanceDataCurrentTimeStep.waterMBR                      */
     double   last_mbe;         /* balanceDataCurrentTimeStep.waterMBE                      */
     uint64_t links;            /* existing links (stored off-diagonals of a full assembly) */
+    uint64_t heat_cap_hits;    /* heat linear solves that stopped at their sweep cap instead of at the
+                                  residual tolerance (cpusolver.cpp:676-700; reference: Gauss-Seidel cap,
+                                  product: 4x that cap of Jacobi sweeps) -- SURVEY Appendix B Q6          */
 } sf3d_counters;
 uint8_t sf3d_ext_get_counters(sf3d_counters *out);
 uint8_t sf3d_ext_reset_counters(void);

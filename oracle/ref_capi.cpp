@@ -12,6 +12,7 @@
  * Heat::GaussSeidelHeatCPU, heat.cpp:664).  The wrappers below count and call the real
  * function; no reference source is edited.
  */
+#include <cmath>
 #include <cstring>
 #include <vector>
 #include "soilFluxes3D.h"      // the reference's own header (-I /root/reference/...)
@@ -30,6 +31,9 @@ namespace soilFluxes3D::v2 {
 }
 
 static sf3d_counters g_cnt;
+/* heat_cap_hits bookkeeping: tolerance and sweep cap of the heat solve (defaults of SolverParameters, types.h:291-315) */
+static double g_tolerance = 1e-10;
+static uint32_t g_heatCap = 200, g_heatSolveSweeps = 0;
 
 /* optional capture of the linear system seen by the last Jacobi call (kernel-level KATs) */
 static int g_capture = 0;
@@ -87,7 +91,13 @@ double __wrap__ZN12soilFluxes3D2v24Heat18GaussSeidelHeatCPUERNS0_9VectorCPUERKNS
     sf::VectorCPU& x, const sf::MatrixCPU& A, const sf::VectorCPU& b)
 {
     ++g_cnt.heat_sweeps;
-    return __real__ZN12soilFluxes3D2v24Heat18GaussSeidelHeatCPUERNS0_9VectorCPUERKNS0_9MatrixCPUERKS2_(x, A, b);
+    const double norm = __real__ZN12soilFluxes3D2v24Heat18GaussSeidelHeatCPUERNS0_9VectorCPUERKNS0_9MatrixCPUERKS2_(x, A, b);
+    /* CPUSolver::solveLinearSystem (cpusolver.cpp:676-700) leaves its loop when the norm is below the
+       tolerance or after calcCurrentMaxIterationNumber(maxApprox - 1) sweeps: count the second exit */
+    ++g_heatSolveSweeps;
+    if (norm < g_tolerance) g_heatSolveSweeps = 0;
+    else if (g_heatSolveSweeps >= g_heatCap) { ++g_cnt.heat_cap_hits; g_heatSolveSweeps = 0; }
+    return norm;
 }
 /* accepted heat sub-steps: Heat::updateHeatBalanceData (heat.cpp:393) is called once per accepted
    heatLoop (cpusolver.cpp:593) */
@@ -123,7 +133,16 @@ uint8_t sf3d_set_soil_properties(uint16_t a, uint8_t b, double c, double d, doub
 { return E8(sf::setSoilProperties(a, b, c, d, e, f, g, h, i, j, k, l)); }
 uint8_t sf3d_set_surface_properties(uint16_t i, double r) { return E8(sf::setSurfaceProperties(i, r)); }
 uint8_t sf3d_set_numerical_parameters(double a, double b, uint16_t c, uint16_t d, uint8_t e, uint8_t f)
-{ return E8(sf::setNumericalParameters(a, b, c, d, e, f)); }
+{
+    /* mirror of the clamps (soilFluxes3D.cpp:491-504) and of Solver::calcCurrentMaxIterationNumber (solver.h:55-59),
+       only for the heat_cap_hits counter */
+    const uint16_t it = c < 20 ? 20 : (c > 1000 ? 1000 : c), ap = d < 1 ? 1 : (d > 50 ? 50 : d);
+    const uint8_t ex = e < 5 ? 5 : (e > 12 ? 12 : e);
+    g_tolerance = std::pow(10.0, -ex);
+    const uint32_t cap = static_cast<uint32_t>(ap * (static_cast<float>(it) / static_cast<float>(ap)));
+    g_heatCap = cap < 25u ? 25u : cap;
+    return E8(sf::setNumericalParameters(a, b, c, d, e, f));
+}
 uint8_t sf3d_set_hydraulic_properties(uint8_t w, uint8_t m, float r)
 { return E8(sf::setHydraulicProperties(static_cast<sf::WRCModel>(w), static_cast<sf::meanType_t>(m), r)); }
 

@@ -17,7 +17,8 @@ def checker():
     """The oracle used as checker: the unmodified reference behind the C ABI when its prebuilt
     library is present (oracle/_ref/, built here from /root/reference and shipped with the
     snapshot), else the CPU restatement (oracle/libsf3d_oracle.so)."""
-    from criteria3d_b200 import ORACLE_LIB, REFERENCE_LIB, SoilFluxes3D
+    from criteria3d_b200 import SoilFluxes3D
+    from oracle import ORACLE_LIB, REFERENCE_LIB
     if REFERENCE_LIB.exists():
         return SoilFluxes3D(REFERENCE_LIB)
     if ORACLE_LIB.exists():

@@ -15,7 +15,8 @@ ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
-from criteria3d_b200 import REFERENCE_LIB, SoilFluxes3D  # noqa: E402
+from criteria3d_b200 import SoilFluxes3D  # noqa: E402
+from oracle import REFERENCE_LIB  # noqa: E402
 from scenarios import HEAT_SCENARIOS, SCENARIOS  # noqa: E402
 
 

@@ -15,7 +15,8 @@ import torch.distributed as dist
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
-from criteria3d_b200 import ORACLE_LIB, REFERENCE_LIB, BoundaryType, Field, SoilFluxes3D, load_product  # noqa: E402
+from criteria3d_b200 import BoundaryType, Field, SoilFluxes3D, load_product  # noqa: E402
+from oracle import ORACLE_LIB, REFERENCE_LIB  # noqa: E402
 from criteria3d_b200.mgpu import setup_slab, wire_ranks  # noqa: E402
 from criteria3d_b200.synth import Catchment, run_hours, set_heat_forcing, setup  # noqa: E402
 

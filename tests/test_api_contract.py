@@ -4,7 +4,8 @@ reference; GPU: product vs oracle."""
 import numpy as np
 import pytest
 
-from criteria3d_b200 import ORACLE_LIB, REFERENCE_LIB, BoundaryType, Field, SoilFluxes3D
+from criteria3d_b200 import BoundaryType, Field, SoilFluxes3D
+from oracle import ORACLE_LIB, REFERENCE_LIB
 from criteria3d_b200.synth import Catchment, setup
 
 

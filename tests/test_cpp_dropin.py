@@ -10,7 +10,8 @@ from pathlib import Path
 
 import pytest
 
-from criteria3d_b200 import PRODUCT_LIB, REFERENCE_LIB
+from criteria3d_b200 import PRODUCT_LIB
+from oracle import REFERENCE_LIB
 
 ROOT = Path(__file__).resolve().parent.parent
 SRC = ROOT / "tests" / "cpp" / "dropin_caller.cpp"

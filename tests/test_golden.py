@@ -6,7 +6,8 @@ from pathlib import Path
 import numpy as np
 import pytest
 
-from criteria3d_b200 import ORACLE_LIB, SoilFluxes3D
+from criteria3d_b200 import SoilFluxes3D
+from oracle import ORACLE_LIB
 from scenarios import HEAT_SCENARIOS, SCENARIOS, compare
 
 GOLDEN = Path(__file__).parent / "golden"

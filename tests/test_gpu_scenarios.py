@@ -23,10 +23,23 @@ def test_heat_scenario(product, checker, name):
     compare(a, b, exact=False)
 
 
+def test_heat_coupled_medium(product, checker):
+    """32 x 32 x 11 coupled run (heat parity past toy sizes); also reports how far the Jacobi heat
+    solve stays from its 4x sweep cap compared with the reference's Gauss-Seidel (Q6)"""
+    from scenarios import heat_coupled_medium
+    a = heat_coupled_medium(product)
+    b = heat_coupled_medium(checker)
+    compare(a, b, exact=False)
+    print(f"[heat_coupled_medium] heat sub-steps {int(a['heat_counters'][0])}, heat sweeps product (Jacobi) "
+          f"{int(a['heat_counters'][1])} vs reference (Gauss-Seidel) {int(b['heat_counters'][1])}, cap hits "
+          f"{int(a['heat_cap_hits'])} / {int(b['heat_cap_hits'])}")
+
+
 def test_culvert_against_restatement(product):
     """culvert boundary: product vs the C restatement (the reference cannot run it)"""
     import numpy as np
-    from criteria3d_b200 import ORACLE_LIB, SoilFluxes3D
+    from criteria3d_b200 import SoilFluxes3D
+    from oracle import ORACLE_LIB
     from scenarios import culvert_outlet
     if not ORACLE_LIB.exists():
         pytest.skip("oracle library not built")

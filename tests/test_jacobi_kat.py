@@ -7,7 +7,8 @@ from pathlib import Path
 import numpy as np
 import pytest
 
-from criteria3d_b200 import ORACLE_LIB, REFERENCE_LIB, SoilFluxes3D
+from criteria3d_b200 import SoilFluxes3D
+from oracle import ORACLE_LIB, REFERENCE_LIB
 
 KAT = Path(__file__).parent / "golden" / "jacobi_kat.npz"
 

@@ -4,7 +4,8 @@ scenario, with one OpenMP thread on both sides.  This is what pins the oracle.""
 import numpy as np
 import pytest
 
-from criteria3d_b200 import ORACLE_LIB, REFERENCE_LIB, SoilFluxes3D
+from criteria3d_b200 import SoilFluxes3D
+from oracle import ORACLE_LIB, REFERENCE_LIB
 from scenarios import HEAT_SCENARIOS, SCENARIOS, compare
 
 ALL = {**SCENARIOS, **HEAT_SCENARIOS}

@@ -9,7 +9,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from criteria3d_b200 import ORACLE_LIB, SoilFluxes3D
+from criteria3d_b200 import SoilFluxes3D
+from oracle import ORACLE_LIB
 from criteria3d_b200.partition import make_slab, slab_catchment, slab_rows
 from criteria3d_b200.synth import Catchment, setup
 
@@ -167,3 +168,18 @@ def test_generic_graph_partition_closure_and_halo(world):
                 if lt[s][g] != 0:
                     acc += loc[p.rank][g2l[int(li[s][g])]]
             assert acc == pytest.approx(want[g], rel=1e-14, abs=1e-12)
+
+
+def test_slab_preconditions_are_checked():
+    """the slab maps assume a fully valid raster and at least one row per rank"""
+    import numpy as np
+    import pytest
+    from criteria3d_b200.partition import make_slab, slab_catchment
+    with pytest.raises(ValueError):
+        make_slab(3, 8, 2, world=4, rank=0)                 # fewer rows than ranks: empty slabs
+    with pytest.raises(ValueError):
+        make_slab(8, 8, 2, world=2, rank=2)
+    slab = make_slab(8, 8, 2, world=2, rank=0)
+    valid = np.ones((slab.local_rows, 8), bool); valid[0, 0] = False
+    with pytest.raises(ValueError):
+        slab_catchment(slab, valid=valid)                   # NODATA cells: node ids follow cell ranks, not row arithmetic

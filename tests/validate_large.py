@@ -12,7 +12,8 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
-from criteria3d_b200 import ORACLE_LIB, REFERENCE_LIB, BoundaryType, Field, SoilFluxes3D, load_product  # noqa: E402
+from criteria3d_b200 import BoundaryType, Field, SoilFluxes3D, load_product  # noqa: E402
+from oracle import ORACLE_LIB, REFERENCE_LIB  # noqa: E402
 from criteria3d_b200.synth import STORM_MM_H, Catchment, run_hours, setup  # noqa: E402
 
 
