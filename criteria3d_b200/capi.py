@@ -256,9 +256,11 @@ _EXT = [
     ("sf3d_ext_set_fixed_temperature", u8, [u32, u32, C.POINTER(dbl), dbl]),
     ("sf3d_ext_get_counters", u8, [C.POINTER(Counters)]),
     ("sf3d_ext_reset_counters", u8, []),
+    ("sf3d_ext_last_error", u8, []),
     ("sf3d_ext_backend", C.c_char_p, []),
     ("sf3d_ext_set_device", u8, [cint]),
     ("sf3d_ext_reset_solver", u8, []),
+    ("sf3d_ext_set_time_step", u8, [dbl]),
     ("sf3d_ext_jacobi_sweep", u8, [u32, u32, C.POINTER(u8), C.POINTER(u32), C.POINTER(dbl), C.POINTER(dbl), C.POINTER(dbl),
                                    C.POINTER(dbl), C.POINTER(dbl), C.POINTER(dbl)]),
     ("sf3d_ext_comm_unique_id", u8, [C.POINTER(u8)]),
@@ -394,8 +396,9 @@ class SoilFluxes3D:
             raise RuntimeError(f"sf3d_ext_comm_unique_id -> {SF3Derror(rc).name}")
         return bytes(buf)
 
-    def comm_init(self, rank: int, world: int, uid: bytes) -> int:
-        buf = (u8 * 128).from_buffer_copy(uid)
+    def comm_init(self, rank: int, world: int, uid: bytes | None) -> int:
+        """uid None: peer memory only, no NCCL communicator"""
+        buf = (u8 * 128).from_buffer_copy(uid) if uid is not None else None
         return self.lib.sf3d_ext_comm_init(rank, world, buf)
 
     def ipc_export(self) -> bytes:
@@ -446,8 +449,15 @@ class SoilFluxes3D:
             raise RuntimeError(f"sf3d_ext_jacobi_sweep -> {SF3Derror(rc).name}")
         return x_out, norm.value
 
+    def last_error(self) -> int:
+        """error of the most recent computeStep / computePeriod (then cleared)"""
+        return self.lib.sf3d_ext_last_error()
+
     def reset_solver(self) -> int:
         return self.lib.sf3d_ext_reset_solver()
+
+    def set_time_step(self, delta_t: float) -> int:
+        return self.lib.sf3d_ext_set_time_step(delta_t)
 
     def stream(self) -> int | None:
         return self.lib.sf3d_ext_stream()

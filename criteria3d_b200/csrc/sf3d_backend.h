@@ -42,6 +42,7 @@ void comm_allreduce(double *devValues, int count, bool isMax, Ctrl *ctrl);
 void comm_mailbox_export(unsigned char out[64]);
 void comm_mailbox_import(int peer, const unsigned char handle[64]);
 void comm_halo(double *x, const Ctrl *ctrl);
+void comm_mark_boundary(uint16_t *pid);     // boundary rows of the fused multi-GPU sweep (after every pattern build)
 void comm_ipc_export(double *x0, double *x1, unsigned char out[128]);
 void comm_ipc_import(int peer, const unsigned char handles[128], uint32_t n, const uint32_t *remoteIdx);
 bool comm_direct_halo();

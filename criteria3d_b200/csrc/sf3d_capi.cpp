@@ -201,6 +201,7 @@ uint8_t sync_to_device(bool finalizeTopology = true)
         k_link_geometry(S.eng.v, &ok);
         if (S.heat) k_heat_geometry(S.eng.v);
         S.patternsOk = k_build_patterns(S.eng.v, S.pid, S.pattern, &S.hotPid, S.hotOff) && getenv("SF3D_EXPLICIT_INDEX") == nullptr;
+        if (S.patternsOk) comm_mark_boundary(S.pid);
         fill_view();
         S.topoDirty = false;
         if (!ok)
@@ -250,6 +251,8 @@ double host_node_K(uint32_t i, double Se) { return sf3d_mualem(node_soil(i), g_p
 #define REQUIRE_INIT_D()  do { if (!S.initialized) return err_value(SF3D_MEMORY_ERROR); } while (0)
 #define REQUIRE_INDEX_D(i) do { if ((i) >= S.N) return err_value(SF3D_INDEX_ERROR); } while (0)
 
+uint8_t g_lastStepError = SF3D_OK;              // sf3d_ext_last_error
+
 template <class F>
 auto guarded(F &&f, decltype(f()) onError) -> decltype(f())
 {
@@ -257,6 +260,7 @@ auto guarded(F &&f, decltype(f()) onError) -> decltype(f())
     catch (const DeviceError &e)
     {
         fprintf(stderr, "[sf3d_b200] device error in %s: %s\n", e.where, e.what);
+        g_lastStepError = SF3D_SOLVER_ERROR;
         return onError;
     }
 }
@@ -901,6 +905,7 @@ double sf3d_get_heat_mbe(void) { return S.eng.wholePeriod.heatMBE; }
 // ---- computation (soilFluxes3D.cpp:1760-1821) ----------------------------------------------------------------------------------
 double sf3d_compute_step(double maxTimeStep)
 {
+    g_lastStepError = SF3D_OK;
     return guarded([&]() -> double {
         if (!S.initialized) return err_value(SF3D_MEMORY_ERROR);
         if (sync_to_device()) return err_value(SF3D_TOPOGRAPHY_ERROR);
@@ -911,6 +916,7 @@ double sf3d_compute_step(double maxTimeStep)
 }
 void sf3d_compute_period(double timePeriod)
 {
+    g_lastStepError = SF3D_OK;
     guarded([&]() -> int {
         if (!S.initialized) return 0;
         if (sync_to_device()) return 0;
@@ -1195,6 +1201,7 @@ uint8_t sf3d_ext_get_counters(sf3d_counters *out)
     return SF3D_OK;
 }
 uint8_t sf3d_ext_reset_counters(void) { memset(&S.eng.cnt, 0, sizeof S.eng.cnt); return SF3D_OK; }
+uint8_t sf3d_ext_last_error(void) { const uint8_t e = g_lastStepError; g_lastStepError = SF3D_OK; return e; }
 const char *sf3d_ext_backend(void) { return "b200"; }
 uint8_t sf3d_ext_set_device(int device)
 {
@@ -1204,6 +1211,7 @@ uint8_t sf3d_ext_set_device(int device)
 }
 
 uint8_t sf3d_ext_reset_solver(void) { g_params = default_params(); return SF3D_OK; }
+uint8_t sf3d_ext_set_time_step(double deltaT) { g_params.deltaTcurr = deltaT; return SF3D_OK; }     // solver.h:77-86
 
 uint8_t sf3d_ext_jacobi_sweep(uint32_t n, uint32_t nSurface, const uint8_t *ncols, const uint32_t *col, const double *val,
                               const double *b, const double *z, const double *xIn, double *xOut, double *norm)
@@ -1249,6 +1257,7 @@ uint8_t sf3d_ext_comm_unique_id(uint8_t id[128])
 uint8_t sf3d_ext_comm_init(int rank, int world, const uint8_t id[128])
 {
     if (S.initialized) return SF3D_PARAMETER_ERROR;     // wire the ranks before initializeSF3D
+    // id == NULL: peer memory only, no NCCL communicator (see comm_init)
     return guarded([&]() -> uint8_t { dev_select(g_device); comm_init(rank, world, id); return SF3D_OK; }, (uint8_t)SF3D_SOLVER_ERROR);
 }
 uint8_t sf3d_ext_ipc_export(uint8_t handles[128])

@@ -20,6 +20,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+#include <algorithm>
 #include "sf3d_backend.h"
 #include "sf3d_rows_heat.h"
 #include "sf3d_fields.h"
@@ -257,7 +258,6 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_heat_geometry(SF3DView v)
 // proves  i + pattern[pid[i]][c] == mcol[c][i]  for every entry (bit-exact integer map) or the
 // explicit index array stays in use.
 #define SF3D_PATTERN_SLOTS 1024
-#define SF3D_GHOST_PID 0xFFFFu      // rows received from a neighbouring slab: never swept
 __device__ __forceinline__ unsigned long long pattern_hash(const int32_t *off)
 {
     unsigned long long h = 0x9E3779B97F4A7C15ull;
@@ -354,10 +354,90 @@ __global__ void __launch_bounds__(SF3D_BLOCK, SF3D_NODE_BLOCKS) kern_node_phase(
         sf3d_row_node_phase<HEAT>(v, i, dt, withCapacity);
 }
 
-// the stopping / Courant rules, applied either by the last block of the producing kernel (single
-// GPU) or by a one-thread kernel after the all-reduce of the local values (row-slab ranks)
+// ---- row-slab ranks: device side of the peer-memory all-reduce ---------------------------------------
+// Every rank owns a mailbox that all ranks can write through CUDA IPC (NVLink peer stores).
+#define SF3D_MAX_RANKS 16
+struct Mbox {
+    double val[2][SF3D_MAX_RANKS][4];
+    unsigned long long seq[2][SF3D_MAX_RANKS];
+    unsigned long long localSeq;        // all-reduces executed by THIS rank so far (only this rank touches it)
+    int error; int pad;
+};
+// kernel parameter of the reducing kernels.  mine == nullptr: the reduction over ranks is finished by separate
+// launches (NCCL, or the separate-kernel peer-memory path kept for A/B), the kernel only leaves its local value
+// in Ctrl::red
+struct CommDev { Mbox *mine; Mbox *const *peers; int rank, world; long long timeoutCycles; };
+
+// All-reduce of up to four doubles over peer memory, executed by ONE warp: lane r stores this rank's values and
+// then the sequence number into rank r's mailbox (system-scope fence in between) and waits until rank r's
+// contribution for the same sequence number has landed in the local mailbox; lane 0 folds the contributions in
+// rank order, so every rank obtains the bit-identical result and takes the same decisions.  The sequence number
+// counts the all-reduces this rank has EXECUTED (device side: launches that return early on every rank, e.g.
+// sweeps enqueued after convergence, do not consume one), so consecutive all-reduces always use different slots
+// and a rank can be at most one all-reduce ahead of its slowest peer.  The wait is bounded
+// (SF3D_MAILBOX_TIMEOUT_S, default 20 s of SM clocks): on expiry Ctrl::commError is set and the status becomes
+// SOLVE_COMM_ERROR, which the host turns into an error return (read_ctrl throws) -- never into a numerical
+// "halve the time step" event.
+__device__ __forceinline__ void p2p_allreduce_warp(const CommDev &cm, int count, int isMax, double *values, Ctrl *ctrl)
+{
+    const int lane = threadIdx.x & 31;
+    unsigned long long seq = 0ull;
+    int timedOut = 0;
+    if (lane == 0) { seq = cm.mine->localSeq + 1ull; cm.mine->localSeq = seq; timedOut = cm.mine->error; }
+    seq = __shfl_sync(0xffffffffu, seq, 0);
+    timedOut = __shfl_sync(0xffffffffu, timedOut, 0);       // sticky: after one time-out no further waiting
+    const int par = (int)(seq & 1ull);
+    if (!timedOut && lane < cm.world)
+    {
+        Mbox *dst = cm.peers[lane];
+        for (int k = 0; k < count; ++k) *((volatile double *)&dst->val[par][cm.rank][k]) = values[k];
+        __threadfence_system();
+        *((volatile unsigned long long *)&dst->seq[par][cm.rank]) = seq;
+        const long long t0 = clock64();
+        while (*((volatile unsigned long long *)&cm.mine->seq[par][lane]) != seq)
+            if (clock64() - t0 > cm.timeoutCycles) { timedOut = 1; break; }
+    }
+    timedOut = __any_sync(0xffffffffu, timedOut);
+    __threadfence_system();
+    if (lane == 0)
+    {
+        if (timedOut)
+        {
+            cm.mine->error = 1;
+            if (ctrl) { ctrl->commError = 1; ctrl->status = SOLVE_COMM_ERROR; }
+        }
+        else
+            for (int k = 0; k < count; ++k)
+            {
+                double acc = *((volatile double *)&cm.mine->val[par][0][k]);
+                for (int r = 1; r < cm.world; ++r)
+                {
+                    const double x = *((volatile double *)&cm.mine->val[par][r][k]);
+                    acc = isMax ? ((acc < x) ? x : acc) : (acc + x);
+                }
+                values[k] = acc;
+            }
+    }
+    __syncwarp();
+}
+__global__ void kern_p2p_allreduce(CommDev cm, int count, int isMax, double *values, Ctrl *ctrl)
+{
+    p2p_allreduce_warp(cm, count, isMax, values, ctrl);
+}
+// called by EVERY thread of the block that finished last, after thread 0 wrote the local values into c->red[]:
+// folds the all-reduce over ranks into the producing kernel (no extra launch per reduction)
+__device__ __forceinline__ void last_block_allreduce(const CommDev &cm, Ctrl *c, int count, int isMax)
+{
+    __syncthreads();
+    if (threadIdx.x < 32) p2p_allreduce_warp(cm, count, isMax, c->red, c);
+    __syncthreads();
+}
+
+// the stopping / Courant rules, applied by the last block of the producing kernel (single GPU, or several GPUs
+// with the in-kernel all-reduce) or by a one-thread kernel after a separately launched all-reduce
 __device__ __forceinline__ void rule_courant(Ctrl *c, double cmax, double dt, double dtMin)
 {
+    if (c->commError) { c->status = SOLVE_COMM_ERROR; return; }
     c->courantMax = cmax;
     const bool ok = (cmax < 1.01) || (dt <= dtMin);      // CPUSolver::checkCourant, cpusolver.cpp:259
     c->status = ok ? SOLVE_RUNNING : SOLVE_COURANT_FAIL;
@@ -367,6 +447,7 @@ __device__ __forceinline__ void rule_courant(Ctrl *c, double cmax, double dt, do
 }
 __device__ __forceinline__ void rule_jacobi(Ctrl *c, double total, double nGlobal, int maxIter, double tol)
 {
+    if (c->commError) { c->status = SOLVE_COMM_ERROR; return; }
     const double curr = total / nGlobal;                      // water.cpp:600
     c->lastNorm = curr;
     c->sweeps += 1;
@@ -401,7 +482,7 @@ __global__ void kern_rule_boundary(Ctrl *c) { c->boundarySum = c->red[0]; }
 #define SF3D_ASSEMBLE_BLOCKS 6
 #endif
 template <bool HEAT>
-__global__ void __launch_bounds__(SF3D_BLOCK, HEAT ? SF3D_HEAT_ASSEMBLE_BLOCKS : SF3D_ASSEMBLE_BLOCKS) kern_assemble(SF3DView v, double dt, int approx, double dtMin)
+__global__ void __launch_bounds__(SF3D_BLOCK, HEAT ? SF3D_HEAT_ASSEMBLE_BLOCKS : SF3D_ASSEMBLE_BLOCKS) kern_assemble(SF3DView v, double dt, int approx, double dtMin, CommDev cm)
 {
     __shared__ double sh[SF3D_BLOCK / 32];
     __shared__ double ksh[SF3D_NLINK * SF3D_BLOCK];          // ten conductances per thread, conflict-free layout
@@ -417,10 +498,12 @@ __global__ void __launch_bounds__(SF3D_BLOCK, HEAT ? SF3D_HEAT_ASSEMBLE_BLOCKS :
     if (last_block(v.ctrl))
     {
         const double cmax = fold_partials<true>(v.partA, sh);
+        const bool inKernel = v.world > 1 && cm.mine != nullptr;
+        if (threadIdx.x == 0) v.ctrl->red[0] = cmax;
+        if (inKernel) last_block_allreduce(cm, v.ctrl, 1, 1);         // max Courant over the ranks
         if (threadIdx.x == 0)
         {
-            if (v.world == 1) rule_courant(v.ctrl, cmax, dt, dtMin);
-            else v.ctrl->red[0] = cmax;
+            if (v.world == 1 || inKernel) rule_courant(v.ctrl, v.ctrl->red[0], dt, dtMin);
             v.ctrl->ticket = 0;
         }
     }
@@ -462,91 +545,81 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_pack(const double *__restrict
 {
     for (uint32_t k = blockIdx.x * SF3D_BLOCK + threadIdx.x; k < n; k += gridDim.x * SF3D_BLOCK) buf[k] = x[idx[k]];
 }
-#define SF3D_MAX_RANKS 16
-struct Mbox { double val[2][SF3D_MAX_RANKS][4]; unsigned long long seq[2][SF3D_MAX_RANKS]; int error; int pad; };
-// All-reduce of up to four doubles over peer memory, one warp per rank: lane r stores this rank's values
-// and then the sequence number into rank r's mailbox (NVLink peer stores, system-scope fence in between),
-// then waits until rank r's contribution for the same sequence number has landed in the local mailbox;
-// lane 0 folds the contributions in rank order, so every rank obtains the bit-identical result.  Two slots
-// by sequence parity: a rank can run at most one call ahead of its slowest peer.  The wait is bounded
-// (about 10 s of SM clocks); on expiry the error flag makes the host abort instead of hanging the GPU.
-__device__ __forceinline__ void p2p_allreduce_warp(Mbox *mine, Mbox *const *peers, int rank, int world, unsigned long long seq,
-                                                   int count, int isMax, double *values, Ctrl *ctrl)
-{
-    const int lane = threadIdx.x & 31;
-    const int par = (int)(seq & 1ull);
-    if (lane < world)
-    {
-        Mbox *dst = peers[lane];
-        for (int k = 0; k < count; ++k) *((volatile double *)&dst->val[par][rank][k]) = values[k];
-        __threadfence_system();
-        *((volatile unsigned long long *)&dst->seq[par][rank]) = seq;
-        const long long t0 = clock64();
-        while (*((volatile unsigned long long *)&mine->seq[par][lane]) != seq)
-            if (clock64() - t0 > 20000000000ll) { mine->error = 1; break; }
-    }
-    __threadfence_system();
-    __syncwarp();
-    if (lane == 0)
-    {
-        for (int k = 0; k < count; ++k)
-        {
-            double acc = *((volatile double *)&mine->val[par][0][k]);
-            for (int r = 1; r < world; ++r)
-            {
-                const double x = *((volatile double *)&mine->val[par][r][k]);
-                acc = isMax ? ((acc < x) ? x : acc) : (acc + x);
-            }
-            values[k] = acc;
-        }
-        if (mine->error && ctrl) ctrl->status = SOLVE_DIVERGED;
-    }
-}
-__global__ void kern_p2p_allreduce(Mbox *mine, Mbox *const *peers, int rank, int world, unsigned long long seq,
-                                   int count, int isMax, double *values, Ctrl *ctrl)
-{
-    p2p_allreduce_warp(mine, peers, rank, world, seq, count, isMax, values, ctrl);
-}
-
-// One kernel per sweep for everything that follows the Jacobi rows on several GPUs: the boundary rows of x
-// go straight into the neighbours' ghost rows (NVLink peer stores); the block that finishes last then
-// all-reduces the residual sum through the mailboxes -- its system-scope fence orders every block's halo
-// stores before the sequence number the peers wait for -- and applies the stopping rule
-// (cpusolver.cpp:678-700).  Replaces kern_push x peers + kern_p2p_allreduce + kern_rule_jacobi.
+// ---- one launch per sweep on several GPUs ---------------------------------------------------------
+// The rows some neighbouring rank holds as ghosts ("boundary rows": the first / last owned DEM row of a slab, all
+// layers) are swept FIRST and their new values stored straight into the neighbours' ghost rows (NVLink peer
+// stores into the neighbour's output buffer of this sweep), so the halo travels while the interior rows are being
+// swept.  Boundary and ghost rows carry SF3D_PID_SKIP in their pattern id, so the interior loop passes over them
+// without an extra load.  The block that finishes last then all-reduces the residual through the mailboxes -- its
+// system-scope fence orders every block's halo stores before the sequence number the peers wait for -- and
+// applies the stopping rule (cpusolver.cpp:678-700).  A peer cannot be overtaken: rank r writes sweep s + 1 into
+// a neighbour's buffer only after the all-reduce of sweep s, i.e. after that neighbour finished reading it.
 #define SF3D_MAX_HALO_PEERS 4
+#define SF3D_NO_REMOTE 0xFFFFFFFFu
 struct ExchangeDev {
+    uint32_t nBoundary;                                 // owned rows that at least one peer holds as ghosts
+    const uint32_t *bIdx;                               // their local ids (unique)
     int nPeers;
-    uint32_t nSend[SF3D_MAX_HALO_PEERS];
-    const uint32_t *sendIdx[SF3D_MAX_HALO_PEERS];
-    const uint32_t *remoteIdx[SF3D_MAX_HALO_PEERS];
-    double *peerX[SF3D_MAX_HALO_PEERS];
+    const uint32_t *remote[SF3D_MAX_HALO_PEERS];        // [nBoundary] id of the row in peer p's numbering, or SF3D_NO_REMOTE
+    double *peerX[SF3D_MAX_HALO_PEERS];                 // peer p's OUTPUT solution buffer of this sweep
 };
-__global__ void __launch_bounds__(SF3D_BLOCK) kern_sweep_exchange(const double *__restrict__ x, ExchangeDev e, Mbox *mine, Mbox *const *peers,
-                                                                  int rank, int world, unsigned long long seq, Ctrl *ctrl,
-                                                                  double nGlobal, int maxIter, double tol)
+__device__ __forceinline__ void rule_heat_jacobi(Ctrl *c, double norm, int maxIter, double tol)
 {
-    if (ctrl->status != SOLVE_RUNNING) return;          // same decision on every rank: the status derives from all-reduced values
-    for (int p = 0; p < e.nPeers; ++p)
+    if (c->commError) { c->status = SOLVE_COMM_ERROR; return; }
+    c->lastNorm = norm;
+    c->sweeps += 1;
+    if (norm < tol) c->status = SOLVE_CONVERGED;              // cpusolver.cpp:692 (no divergence test for heat)
+    else if (c->sweeps >= maxIter) c->status = SOLVE_MAXITER;
+}
+template <bool HEAT>
+__global__ void __launch_bounds__(SF3D_BLOCK, SF3D_JACOBI_BLOCKS) kern_jacobi_multi(SF3DView v, const double *__restrict__ xin,
+                                                                                double *__restrict__ xout, int maxIter, double tol,
+                                                                                ExchangeDev e, CommDev cm)
+{
+    if (v.ctrl->status != SOLVE_RUNNING) return;        // same decision on every rank: the status derives from all-reduced values
+    __shared__ double sh[SF3D_BLOCK / 32];
+    double norm = 0.;
+    for (uint32_t k = blockIdx.x * SF3D_BLOCK + threadIdx.x; k < e.nBoundary; k += gridDim.x * SF3D_BLOCK)
     {
-        const uint32_t *__restrict__ idx = e.sendIdx[p];
-        const uint32_t *__restrict__ rem = e.remoteIdx[p];
-        double *__restrict__ dst = e.peerX[p];
-        for (uint32_t k = blockIdx.x * SF3D_BLOCK + threadIdx.x; k < e.nSend[p]; k += gridDim.x * SF3D_BLOCK) dst[rem[k]] = x[idx[k]];
+        const uint32_t i = e.bIdx[k];
+        double xn;
+        const double d = HEAT ? sf3d_row_heat_jacobi(v, i, xin, xout, &xn) : sf3d_row_jacobi(v, i, xin, xout, &xn);
+        norm = HEAT ? ((norm < d) ? d : norm) : (norm + d);
+        for (int p = 0; p < e.nPeers; ++p)
+        {
+            const uint32_t r = e.remote[p][k];
+            if (r != SF3D_NO_REMOTE) e.peerX[p][r] = xn;
+        }
     }
-    __threadfence_system();
-    if (!last_block(ctrl)) return;
-    if (threadIdx.x < 32)
+    for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
     {
-        p2p_allreduce_warp(mine, peers, rank, world, seq, 1, 0, ctrl->red, ctrl);
+        if (v.pid[i] & SF3D_PID_SKIP) continue;         // ghost row, or boundary row already done above
+        const double d = HEAT ? sf3d_row_heat_jacobi(v, i, xin, xout) : sf3d_row_jacobi(v, i, xin, xout);
+        norm = HEAT ? ((norm < d) ? d : norm) : (norm + d);
+    }
+    norm = block_reduce<HEAT>(norm, sh);
+    if (threadIdx.x == 0) v.partA[blockIdx.x] = norm;
+    __threadfence_system();                             // this block's peer stores before its ticket
+    if (last_block(v.ctrl))
+    {
+        const double total = fold_partials<HEAT>(v.partA, sh);
+        if (threadIdx.x == 0) v.ctrl->red[0] = total;
+        last_block_allreduce(cm, v.ctrl, 1, HEAT ? 1 : 0);
         if (threadIdx.x == 0)
         {
-            if (ctrl->status == SOLVE_RUNNING) rule_jacobi(ctrl, ctrl->red[0], nGlobal, maxIter, tol);
-            ctrl->ticket = 0;
+            if (HEAT) rule_heat_jacobi(v.ctrl, v.ctrl->red[0], maxIter, tol);
+            else rule_jacobi(v.ctrl, v.ctrl->red[0], v.nGlobal, maxIter, tol);
+            v.ctrl->ticket = 0;
         }
     }
 }
+__global__ void __launch_bounds__(SF3D_BLOCK) kern_mark_boundary(uint16_t *pid, const uint32_t *__restrict__ idx, uint32_t n)
+{
+    for (uint32_t k = blockIdx.x * SF3D_BLOCK + threadIdx.x; k < n; k += gridDim.x * SF3D_BLOCK) pid[idx[k]] |= (uint16_t)SF3D_PID_SKIP;
+}
 
-// direct halo: store my boundary values into the neighbour's ghost entries (peer memory, NVLink)
+// direct halo, separate-kernel form (A/B of the fused sweep): store my boundary values into the neighbour's ghost
+// entries (peer memory, NVLink)
 __global__ void __launch_bounds__(SF3D_BLOCK) kern_push(const double *__restrict__ x, const uint32_t *__restrict__ idx, uint32_t n,
                                                       double *__restrict__ peerX, const uint32_t *__restrict__ remoteIdx,
                                                       const Ctrl *ctrl)
@@ -562,7 +635,7 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_unpack(double *__restrict__ x
 }
 
 // H = x, Se refresh, and the two mass-balance sums
-__global__ void __launch_bounds__(SF3D_BLOCK, SF3D_POST_BLOCKS) kern_post(SF3DView v, const double *__restrict__ x, double dt, int mode)
+__global__ void __launch_bounds__(SF3D_BLOCK, SF3D_POST_BLOCKS) kern_post(SF3DView v, const double *__restrict__ x, double dt, int mode, CommDev cm)
 {
     __shared__ double sh[SF3D_BLOCK / 32];
     double storage = 0., sinkSum = 0.;
@@ -581,10 +654,12 @@ __global__ void __launch_bounds__(SF3D_BLOCK, SF3D_POST_BLOCKS) kern_post(SF3DVi
     {
         const double st = fold_partials<false>(v.partA, sh);
         const double sk = fold_partials<false>(v.partB, sh);
+        const bool inKernel = v.world > 1 && cm.mine != nullptr;
+        if (threadIdx.x == 0) { v.ctrl->red[0] = st; v.ctrl->red[1] = sk; }
+        if (inKernel) last_block_allreduce(cm, v.ctrl, 2, 0);
         if (threadIdx.x == 0)
         {
-            if (v.world == 1) { v.ctrl->storage = st; v.ctrl->sinkSum = sk; }
-            else { v.ctrl->red[0] = st; v.ctrl->red[1] = sk; }
+            if (v.world == 1 || inKernel) { v.ctrl->storage = v.ctrl->red[0]; v.ctrl->sinkSum = v.ctrl->red[1]; }
             v.ctrl->ticket = 0;
         }
     }
@@ -603,7 +678,7 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_restore_best(SF3DView v)
 }
 
 // getTotalBoundaryWaterFlow (soilFluxes3D.cpp:1240-1250)
-__global__ void __launch_bounds__(SF3D_BLOCK) kern_total_boundary(SF3DView v, uint32_t bt)
+__global__ void __launch_bounds__(SF3D_BLOCK) kern_total_boundary(SF3DView v, uint32_t bt, CommDev cm)
 {
     __shared__ double sh[SF3D_BLOCK / 32];
     double sum = 0.;
@@ -614,9 +689,12 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_total_boundary(SF3DView v, ui
     if (last_block(v.ctrl))
     {
         const double t = fold_partials<false>(v.partA, sh);
+        const bool inKernel = v.world > 1 && cm.mine != nullptr;
+        if (threadIdx.x == 0) v.ctrl->red[0] = t;
+        if (inKernel) last_block_allreduce(cm, v.ctrl, 1, 0);
         if (threadIdx.x == 0)
         {
-            if (v.world == 1) v.ctrl->boundarySum = t; else v.ctrl->red[0] = t;
+            if (v.world == 1 || inKernel) v.ctrl->boundarySum = v.ctrl->red[0];
             v.ctrl->ticket = 0;
         }
     }
@@ -797,7 +875,7 @@ __global__ void __launch_bounds__(SF3D_BLOCK, SF3D_HEAT_BLOCKS) kern_save_water_
         sf3d_row_save_water_fluxes(v, i, dtHeat, dtWater);
 }
 // updateBoundaryHeatData: heat flux per node + max heat-boundary Courant (heat.cpp:237-340)
-__global__ void __launch_bounds__(SF3D_BLOCK, SF3D_HEAT_BLOCKS) kern_boundary_heat(SF3DView v, double maxTimeStep)
+__global__ void __launch_bounds__(SF3D_BLOCK, SF3D_HEAT_BLOCKS) kern_boundary_heat(SF3DView v, double maxTimeStep, CommDev cm)
 {
     __shared__ double sh[SF3D_BLOCK / 32];
     double courant = 0.;
@@ -811,7 +889,10 @@ __global__ void __launch_bounds__(SF3D_BLOCK, SF3D_HEAT_BLOCKS) kern_boundary_he
     if (last_block(v.ctrl))
     {
         const double cmax = fold_partials<true>(v.partA, sh);
-        if (threadIdx.x == 0) { v.ctrl->heatCourantMax = cmax; v.ctrl->red[0] = cmax; v.ctrl->ticket = 0; }
+        const bool inKernel = v.world > 1 && cm.mine != nullptr;
+        if (threadIdx.x == 0) v.ctrl->red[0] = cmax;
+        if (inKernel) last_block_allreduce(cm, v.ctrl, 1, 1);
+        if (threadIdx.x == 0) { v.ctrl->heatCourantMax = v.ctrl->red[0]; v.ctrl->ticket = 0; }
     }
 }
 __global__ void kern_rule_heat_courant(Ctrl *c) { c->heatCourantMax = c->red[0]; }
@@ -833,13 +914,6 @@ __global__ void __launch_bounds__(SF3D_BLOCK, SF3D_HEAT_BLOCKS) kern_heat_assemb
 {
     for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
         if (!(v.world > 1 && META_GHOST(v.meta[i]))) sf3d_row_heat_assemble(v, i, dtHeat, dtWater);
-}
-__device__ __forceinline__ void rule_heat_jacobi(Ctrl *c, double norm, int maxIter, double tol)
-{
-    c->lastNorm = norm;
-    c->sweeps += 1;
-    if (norm < tol) c->status = SOLVE_CONVERGED;              // cpusolver.cpp:692 (no divergence test for heat)
-    else if (c->sweeps >= maxIter) c->status = SOLVE_MAXITER;
 }
 __global__ void kern_rule_heat_jacobi(Ctrl *c, int maxIter, double tol)
 {
@@ -872,7 +946,7 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_heat_jacobi(SF3DView v, const
     }
 }
 __global__ void __launch_bounds__(SF3D_BLOCK, SF3D_HEAT_BLOCKS) kern_heat_post(SF3DView v, const double *__restrict__ x, double dtHeat,
-                                                             double dtWater, int mode)
+                                                             double dtWater, int mode, CommDev cm)
 {
     __shared__ double sh[SF3D_BLOCK / 32];
     double storage = 0., sinkSum = 0.;
@@ -890,10 +964,12 @@ __global__ void __launch_bounds__(SF3D_BLOCK, SF3D_HEAT_BLOCKS) kern_heat_post(S
     {
         const double st = fold_partials<false>(v.partA, sh);
         const double sk = fold_partials<false>(v.partB, sh);
+        const bool inKernel = v.world > 1 && cm.mine != nullptr;
+        if (threadIdx.x == 0) { v.ctrl->red[0] = st; v.ctrl->red[1] = sk; }
+        if (inKernel) last_block_allreduce(cm, v.ctrl, 2, 0);
         if (threadIdx.x == 0)
         {
-            if (v.world == 1) { v.ctrl->heatStorage = st; v.ctrl->heatSinkSum = sk; }
-            else { v.ctrl->red[0] = st; v.ctrl->red[1] = sk; }
+            if (v.world == 1 || inKernel) { v.ctrl->heatStorage = v.ctrl->red[0]; v.ctrl->heatSinkSum = v.ctrl->red[1]; }
             v.ctrl->ticket = 0;
         }
     }
@@ -962,13 +1038,19 @@ struct HaloPeer {
     // direct mode: the neighbour's two solution buffers mapped through CUDA IPC, and where each of my
     // send entries lives in the neighbour's numbering (its ghost row)
     double *peerX[2]; uint32_t *remoteIdx;
+    std::vector<uint32_t> hostSend, hostRemote;     // host copies, for the boundary-row table of the fused sweep
 };
 // direct reductions: every rank owns a mailbox that all ranks can write through CUDA IPC
 static Mbox *g_mbox = nullptr;                       // this rank's mailbox (device memory)
 static Mbox *g_peerMbox[SF3D_MAX_RANKS] = {nullptr}; // host copy of the mapped pointers ([g_rank] = g_mbox)
 static Mbox **g_peerMboxDev = nullptr;               // the same table in device memory
-static unsigned long long g_seq = 0;
 static bool g_directReduce = false;
+static long long g_timeoutCycles = 0;               // bound of the mailbox wait, SM clocks
+// fused sweep: the unique boundary rows and, per peer, where each of them lives in the peer's numbering
+static uint32_t *g_bIdx = nullptr; static uint32_t g_nBoundary = 0;
+static uint32_t *g_bRemote[SF3D_MAX_HALO_PEERS] = {nullptr};
+static bool g_exchangeReady = false;
+static bool separate_kernels() { static const bool v = getenv("SF3D_FUSED_EXCHANGE") && atoi(getenv("SF3D_FUSED_EXCHANGE")) == 0; return v; }
 static double *g_localX[2] = {nullptr, nullptr};     // this rank's x0 / x1 (exported to the neighbours)
 static bool g_directHalo = false;
 static std::vector<HaloPeer> g_halo;
@@ -1007,16 +1089,29 @@ void comm_unique_id(unsigned char out[128])
     NCCL_OK(nccl.GetUniqueId(&id));
     memcpy(out, id.internal, 128);
 }
+// idBytes == nullptr: no NCCL communicator (peer memory only: the direct halo and the mailbox all-reduce must be
+// wired before the first step; used where NCCL cannot run, e.g. several ranks sharing one device in the tests)
 void comm_init(int rank, int world, const unsigned char idBytes[128])
 {
     ensure_device();
-    nccl_load();
     if (g_comm) { nccl.CommDestroy(g_comm); g_comm = nullptr; }
-    ncclUniqueId id;
-    memcpy(id.internal, idBytes, 128);
-    NCCL_OK(nccl.CommInitRank(&g_comm, world, id, rank));
+    if (idBytes)
+    {
+        nccl_load();
+        ncclUniqueId id;
+        memcpy(id.internal, idBytes, 128);
+        NCCL_OK(nccl.CommInitRank(&g_comm, world, id, rank));
+    }
     g_rank = rank; g_world = world;
+    // bound of the mailbox wait in SM clocks
+    double seconds = 20.;
+    if (const char *e = getenv("SF3D_MAILBOX_TIMEOUT_S")) { const double t = atof(e); if (t > 0.) seconds = t; }
+    int khz = 0;
+    CUDA_OK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, g_device));
+    g_timeoutCycles = (long long)(seconds * 1e3 * (double)khz);
 }
+static void require_nccl(const char *what)
+{ if (!g_comm) throw DeviceError{-4, "no NCCL communicator and the peer-memory path is not wired", what}; }
 int comm_world() { return g_world; }
 int comm_rank() { return g_rank; }
 void comm_clear_halo()
@@ -1031,9 +1126,12 @@ void comm_clear_halo()
     for (int r = 0; r < SF3D_MAX_RANKS; ++r)
         if (g_peerMbox[r] && r != g_rank) { cudaIpcCloseMemHandle(g_peerMbox[r]); }
     for (int r = 0; r < SF3D_MAX_RANKS; ++r) g_peerMbox[r] = nullptr;
-    dev_free(g_mbox); g_mbox = nullptr;
+    dev_free(g_mbox); g_mbox = nullptr;             // a fresh mailbox starts with sequence 0 and no error
     dev_free(g_peerMboxDev); g_peerMboxDev = nullptr;
-    g_directReduce = false; g_seq = 0;
+    g_directReduce = false;
+    dev_free(g_bIdx); g_bIdx = nullptr; g_nBoundary = 0;
+    for (int p = 0; p < SF3D_MAX_HALO_PEERS; ++p) { dev_free(g_bRemote[p]); g_bRemote[p] = nullptr; }
+    g_exchangeReady = false;
 }
 // direct reductions: export this rank's mailbox / import the others'
 void comm_mailbox_export(unsigned char out[64])
@@ -1092,6 +1190,8 @@ void comm_ipc_import(int peer, const unsigned char handles[128], uint32_t n, con
         }
         h.remoteIdx = (uint32_t *)dev_alloc((size_t)n * 4);
         if (n) h2d(h.remoteIdx, remoteIdx, (size_t)n * 4);
+        h.hostRemote.assign(remoteIdx, remoteIdx + n);
+        g_exchangeReady = false;
         bool all = true;
         for (HaloPeer &q : g_halo) if (!q.peerX[0] || !q.peerX[1]) all = false;
         g_directHalo = all;
@@ -1114,41 +1214,89 @@ void comm_add_halo_peer(int peer, uint32_t nSend, const uint32_t *sendIdx, uint3
     h.sendBuf = (double *)dev_alloc((size_t)nSend * 8); h.recvBuf = (double *)dev_alloc((size_t)nRecv * 8);
     if (nSend) h2d(h.sendIdx, sendIdx, (size_t)nSend * 4);
     if (nRecv) h2d(h.recvIdx, recvIdx, (size_t)nRecv * 4);
+    h.hostSend.assign(sendIdx, sendIdx + nSend);
     g_halo.push_back(h);
+    g_exchangeReady = false;
+}
+static CommDev comm_dev_full()
+{
+    CommDev c{};
+    c.mine = g_mbox; c.peers = g_peerMboxDev; c.rank = g_rank; c.world = g_world; c.timeoutCycles = g_timeoutCycles;
+    return c;
+}
+// what the reducing kernels receive: the mailboxes when the all-reduce over ranks runs inside the producing kernel
+static CommDev comm_dev()
+{
+    if (g_world > 1 && g_directReduce && !separate_kernels()) return comm_dev_full();
+    return CommDev{};
 }
 void comm_allreduce(double *devValues, int count, bool isMax, Ctrl *ctrl)
 {
     if (g_world <= 1) return;
     if (g_directReduce)
     {
-        ++g_seq;
-        kern_p2p_allreduce<<<1, 32, 0, g_stream>>>(g_mbox, g_peerMboxDev, g_rank, g_world, g_seq, count, isMax ? 1 : 0, devValues, ctrl);
+        kern_p2p_allreduce<<<1, 32, 0, g_stream>>>(comm_dev_full(), count, isMax ? 1 : 0, devValues, ctrl);
         LAUNCH_CHECK();
         return;
     }
+    require_nccl("comm_allreduce");
     NCCL_OK(nccl.AllReduce(devValues, devValues, (size_t)count, NCCL_FLOAT64, isMax ? NCCL_MAX : NCCL_SUM, g_comm, g_stream));
 }
-// direct halo + direct reduce + at most SF3D_MAX_HALO_PEERS neighbours: the fused exchange kernel
-bool comm_sweep_exchange(double *x, Ctrl *ctrl, double nGlobal, int maxIter, double tol)
+// the unique boundary rows of this rank (union of the send lists, ascending) and their ids on every peer
+static std::vector<uint32_t> boundary_rows()
 {
-    static const bool disabled = getenv("SF3D_FUSED_EXCHANGE") && atoi(getenv("SF3D_FUSED_EXCHANGE")) == 0;
-    if (disabled || g_world <= 1 || !g_directHalo || !g_directReduce || g_halo.size() > SF3D_MAX_HALO_PEERS) return false;
-    const int b = (x == g_localX[1]) ? 1 : 0;
-    ExchangeDev e{};
-    uint32_t most = 1;
-    for (HaloPeer &h : g_halo)
+    std::vector<uint32_t> all;
+    for (const HaloPeer &h : g_halo) all.insert(all.end(), h.hostSend.begin(), h.hostSend.end());
+    std::sort(all.begin(), all.end());
+    all.erase(std::unique(all.begin(), all.end()), all.end());
+    return all;
+}
+// pattern ids: boundary rows are skipped by the interior loop of the fused sweep (harmless for every other kernel,
+// which mask the bit).  Called after every (re)build of the pattern ids.
+void comm_mark_boundary(uint16_t *pid)
+{
+    if (g_world <= 1 || g_halo.empty() || !pid) return;
+    const std::vector<uint32_t> rows = boundary_rows();
+    if (rows.empty()) return;
+    dev_free(g_bIdx);
+    g_bIdx = (uint32_t *)dev_alloc(rows.size() * 4);
+    h2d(g_bIdx, rows.data(), rows.size() * 4);
+    g_nBoundary = (uint32_t)rows.size();
+    kern_mark_boundary<<<reduce_blocks(g_nBoundary), SF3D_BLOCK, 0, g_stream>>>(pid, g_bIdx, g_nBoundary); LAUNCH_CHECK();
+    g_exchangeReady = false;
+}
+// fused sweep available: peer-memory halo and mailboxes wired, pattern ids in use and marked, few enough neighbours
+static bool exchange_ready(const SF3DView &v)
+{
+    if (separate_kernels() || g_world <= 1 || !g_directHalo || !g_directReduce || !v.pid || !g_bIdx) return false;
+    if (g_halo.size() > SF3D_MAX_HALO_PEERS) return false;
+    if (g_exchangeReady) return true;
+    const std::vector<uint32_t> rows = boundary_rows();
+    if (rows.size() != g_nBoundary) return false;
+    for (size_t p = 0; p < g_halo.size(); ++p)
     {
-        if (!h.nSend) continue;
-        const int p = e.nPeers++;
-        e.nSend[p] = h.nSend; e.sendIdx[p] = h.sendIdx; e.remoteIdx[p] = h.remoteIdx; e.peerX[p] = h.peerX[b];
-        most = h.nSend > most ? h.nSend : most;
+        const HaloPeer &h = g_halo[p];
+        if (h.hostRemote.size() != h.hostSend.size()) return false;
+        std::vector<uint32_t> rem(rows.size(), SF3D_NO_REMOTE);
+        for (size_t k = 0; k < h.hostSend.size(); ++k)
+        {
+            const size_t at = (size_t)(std::lower_bound(rows.begin(), rows.end(), h.hostSend[k]) - rows.begin());
+            rem[at] = h.hostRemote[k];
+        }
+        dev_free(g_bRemote[p]);
+        g_bRemote[p] = (uint32_t *)dev_alloc(rem.size() * 4);
+        h2d(g_bRemote[p], rem.data(), rem.size() * 4);
     }
-    int blocks = reduce_blocks(most);
-    if (blocks > 148) blocks = 148;
-    ++g_seq;
-    kern_sweep_exchange<<<blocks, SF3D_BLOCK, 0, g_stream>>>(x, e, g_mbox, g_peerMboxDev, g_rank, g_world, g_seq, ctrl, nGlobal, maxIter, tol);
-    LAUNCH_CHECK();
+    g_exchangeReady = true;
     return true;
+}
+static ExchangeDev exchange_dev(const double *xout)
+{
+    const int b = (xout == g_localX[1]) ? 1 : 0;
+    ExchangeDev e{};
+    e.nBoundary = g_nBoundary; e.bIdx = g_bIdx; e.nPeers = (int)g_halo.size();
+    for (size_t p = 0; p < g_halo.size(); ++p) { e.remote[p] = g_bRemote[p]; e.peerX[p] = g_halo[p].peerX[b]; }
+    return e;
 }
 void comm_halo(double *x, const Ctrl *ctrl)
 {
@@ -1162,6 +1310,7 @@ void comm_halo(double *x, const Ctrl *ctrl)
             if (h.nSend) { kern_push<<<reduce_blocks(h.nSend), SF3D_BLOCK, 0, g_stream>>>(x, h.sendIdx, h.nSend, h.peerX[b], h.remoteIdx, ctrl); LAUNCH_CHECK(); }
         return;
     }
+    require_nccl("comm_halo");
     for (HaloPeer &h : g_halo)
         if (h.nSend) { kern_pack<<<reduce_blocks(h.nSend), SF3D_BLOCK, 0, g_stream>>>(x, h.sendIdx, h.nSend, h.sendBuf); LAUNCH_CHECK(); }
     NCCL_OK(nccl.GroupStart());
@@ -1232,13 +1381,14 @@ void k_node_phase(const SF3DView &v, double dt, int withCapacity)
 }
 void k_assemble(const SF3DView &v, double dt, int approx, double dtMin)
 {
+    const CommDev cm = comm_dev();
     {
         ProfScope ps(SF3D_K_ASSEMBLE);
-        if (v.computeHeat) kern_assemble<true><<<WIDE_GRID(v.N)>>>(v, dt, approx, dtMin);
-        else kern_assemble<false><<<WIDE_GRID(v.N)>>>(v, dt, approx, dtMin);
+        if (v.computeHeat) kern_assemble<true><<<WIDE_GRID(v.N)>>>(v, dt, approx, dtMin, cm);
+        else kern_assemble<false><<<WIDE_GRID(v.N)>>>(v, dt, approx, dtMin, cm);
         LAUNCH_CHECK();
     }
-    if (v.world > 1)
+    if (v.world > 1 && !cm.mine)
     {
         comm_allreduce(v.ctrl->red, 1, true, v.ctrl);
         kern_rule_courant<<<1, 1, 0, g_stream>>>(v.ctrl, dt, dtMin); LAUNCH_CHECK();
@@ -1246,11 +1396,17 @@ void k_assemble(const SF3DView &v, double dt, int approx, double dtMin)
 }
 void k_jacobi(const SF3DView &v, const double *xin, double *xout, int maxIter, double tol)
 {
+    if (v.world > 1 && exchange_ready(v))
+    {
+        // one launch per sweep: boundary rows first (peer stores), interior rows, in-kernel all-reduce + stopping rule
+        ProfScope ps(SF3D_K_JACOBI);
+        kern_jacobi_multi<false><<<GRID(v.N)>>>(v, xin, xout, maxIter, tol, exchange_dev(xout), comm_dev_full()); LAUNCH_CHECK();
+        return;
+    }
     { ProfScope ps(SF3D_K_JACOBI); kern_jacobi<<<GRID(v.N)>>>(v, xin, xout, maxIter, tol); LAUNCH_CHECK(); }
     if (v.world > 1)
     {
         ProfScope ps(SF3D_K_COMM);
-        if (comm_sweep_exchange(xout, v.ctrl, v.nGlobal, maxIter, tol)) return;      // one fused kernel over peer memory
         comm_halo(xout, v.ctrl);                         // boundary rows of x -> neighbours' ghost rows
         comm_allreduce(v.ctrl->red, 1, false, v.ctrl);           // residual sum over ranks
         kern_rule_jacobi<<<1, 1, 0, g_stream>>>(v.ctrl, v.nGlobal, maxIter, tol); LAUNCH_CHECK();
@@ -1258,8 +1414,9 @@ void k_jacobi(const SF3DView &v, const double *xin, double *xout, int maxIter, d
 }
 void k_post(const SF3DView &v, const double *x, double dt, int mode)
 {
-    { ProfScope ps(SF3D_K_POST); kern_post<<<GRID(v.N)>>>(v, x, dt, mode); LAUNCH_CHECK(); }
-    if (v.world > 1)
+    const CommDev cm = comm_dev();
+    { ProfScope ps(SF3D_K_POST); kern_post<<<GRID(v.N)>>>(v, x, dt, mode, cm); LAUNCH_CHECK(); }
+    if (v.world > 1 && !cm.mine)
     {
         comm_allreduce(v.ctrl->red, 2, false, v.ctrl);
         kern_rule_post<<<1, 1, 0, g_stream>>>(v.ctrl); LAUNCH_CHECK();
@@ -1269,8 +1426,9 @@ void k_accept(const SF3DView &v, double dt) { ProfScope ps(SF3D_K_ACCEPT); kern_
 void k_restore_best(const SF3DView &v) { ProfScope ps(SF3D_K_OTHER); kern_restore_best<<<GRID(v.N)>>>(v); LAUNCH_CHECK(); }
 void k_total_boundary_flow(const SF3DView &v, uint32_t bt)
 {
-    kern_total_boundary<<<GRID(v.N)>>>(v, bt); LAUNCH_CHECK();
-    if (v.world > 1)
+    const CommDev cm = comm_dev();
+    kern_total_boundary<<<GRID(v.N)>>>(v, bt, cm); LAUNCH_CHECK();
+    if (v.world > 1 && !cm.mine)
     {
         comm_allreduce(v.ctrl->red, 1, false, v.ctrl);
         kern_rule_boundary<<<1, 1, 0, g_stream>>>(v.ctrl); LAUNCH_CHECK();
@@ -1308,8 +1466,9 @@ void k_reset_water_fluxes(const SF3DView &v) { if (v.hfSaveMode == 2) { kern_res
 void k_boundary_heat(const SF3DView &v, double maxTimeStep)
 {
     ProfScope ps(SF3D_K_HEAT_BOUNDARY);
-    kern_boundary_heat<<<GRID(v.N)>>>(v, maxTimeStep); LAUNCH_CHECK();
-    if (v.world > 1) { comm_allreduce(v.ctrl->red, 1, true, v.ctrl); kern_rule_heat_courant<<<1, 1, 0, g_stream>>>(v.ctrl); LAUNCH_CHECK(); }
+    const CommDev cm = comm_dev();
+    kern_boundary_heat<<<GRID(v.N)>>>(v, maxTimeStep, cm); LAUNCH_CHECK();
+    if (v.world > 1 && !cm.mine) { comm_allreduce(v.ctrl->red, 1, true, v.ctrl); kern_rule_heat_courant<<<1, 1, 0, g_stream>>>(v.ctrl); LAUNCH_CHECK(); }
 }
 void k_heat_begin(const SF3DView &v, double dtHeat, double dtWater)
 {
@@ -1322,6 +1481,11 @@ void k_heat_assemble(const SF3DView &v, double dtHeat, double dtWater)
 void k_heat_jacobi(const SF3DView &v, const double *xin, double *xout, int maxIter, double tol)
 {
     ProfScope ps(SF3D_K_HEAT_JACOBI);
+    if (v.world > 1 && exchange_ready(v))
+    {
+        kern_jacobi_multi<true><<<GRID(v.N)>>>(v, xin, xout, maxIter, tol, exchange_dev(xout), comm_dev_full()); LAUNCH_CHECK();
+        return;
+    }
     kern_heat_jacobi<<<GRID(v.N)>>>(v, xin, xout, maxIter, tol); LAUNCH_CHECK();
     if (v.world > 1)
     {
@@ -1333,8 +1497,9 @@ void k_heat_jacobi(const SF3DView &v, const double *xin, double *xout, int maxIt
 void k_heat_post(const SF3DView &v, const double *x, double dtHeat, double dtWater, int mode)
 {
     ProfScope ps(SF3D_K_HEAT_POST);
-    kern_heat_post<<<GRID(v.N)>>>(v, x, dtHeat, dtWater, mode); LAUNCH_CHECK();
-    if (v.world > 1) { comm_allreduce(v.ctrl->red, 2, false, v.ctrl); kern_rule_heat_post<<<1, 1, 0, g_stream>>>(v.ctrl); LAUNCH_CHECK(); }
+    const CommDev cm = comm_dev();
+    kern_heat_post<<<GRID(v.N)>>>(v, x, dtHeat, dtWater, mode, cm); LAUNCH_CHECK();
+    if (v.world > 1 && !cm.mine) { comm_allreduce(v.ctrl->red, 2, false, v.ctrl); kern_rule_heat_post<<<1, 1, 0, g_stream>>>(v.ctrl); LAUNCH_CHECK(); }
 }
 void k_heat_accept(const SF3DView &v, double dtHeat, double dtWater)
 { ProfScope ps(SF3D_K_HEAT_ACCEPT); kern_heat_accept<<<GRID(v.N)>>>(v, dtHeat, dtWater); LAUNCH_CHECK(); }
@@ -1358,6 +1523,9 @@ void read_ctrl(const SF3DView &v, Ctrl *out)
     CUDA_OK(cudaStreamSynchronize(g_stream));
     if (g_prof && g_pending.size() > 4096) prof_resolve();
     *out = *g_ctrlPinned;
+    if (out->commError)
+        throw DeviceError{-3, "a row-slab peer did not answer within the mailbox time-out (SF3D_MAILBOX_TIMEOUT_S): "
+                              "the step was abandoned, the state is undefined", "all-reduce over ranks"};
 }
 void write_ctrl(const SF3DView &v, const Ctrl *in)
 {

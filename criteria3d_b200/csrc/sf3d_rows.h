@@ -415,7 +415,7 @@ SF3D_HD void sf3d_row_cols(const SF3DView &v, uint32_t i, uint32_t *j)
 {
     if (v.pid)
     {
-        const uint32_t p = v.pid[i];
+        const uint32_t p = v.pid[i] & SF3D_PID_MASK;
         if (p == v.hotPid)
         {
             #pragma unroll
@@ -439,7 +439,7 @@ SF3D_HD void sf3d_row_cols(const SF3DView &v, uint32_t i, uint32_t *j)
 // and the assembly kernel is bound by fp64 issue, not by these L1-resident loads)
 SF3D_HD const int32_t *sf3d_row_pattern(const SF3DView &v, uint32_t i)
 {
-    return v.pid ? v.pattern + (size_t)v.pid[i] * SF3D_NLINK : nullptr;
+    return v.pid ? v.pattern + (size_t)(v.pid[i] & SF3D_PID_MASK) * SF3D_NLINK : nullptr;
 }
 SF3D_HD uint32_t sf3d_col_index(const SF3DView &v, const int32_t *__restrict__ off, uint32_t i, int c)
 {
@@ -544,7 +544,8 @@ SF3D_HD double sf3d_row_assemble(const SF3DView &v, uint32_t i, double dt, int a
 // ==========================================================================================
 // Water::JacobiWaterCPU, one row (water.cpp:570-596).  Returns the row's contribution to the norm.
 // ==========================================================================================
-SF3D_HD double sf3d_row_jacobi(const SF3DView &v, uint32_t i, const double *__restrict__ xin, double *__restrict__ xout)
+SF3D_HD double sf3d_row_jacobi(const SF3DView &v, uint32_t i, const double *__restrict__ xin, double *__restrict__ xout,
+                               double *xnewOut = nullptr)
 {
     const size_t N = v.N;
     uint32_t j[SF3D_NLINK];
@@ -563,6 +564,7 @@ SF3D_HD double sf3d_row_jacobi(const SF3DView &v, uint32_t i, const double *__re
     const double psi = fabs(xnew - z);
     if (psi > 1.) norm *= (1. / psi);
     xout[i] = xnew;
+    if (xnewOut) *xnewOut = xnew;
     return norm;
 }
 

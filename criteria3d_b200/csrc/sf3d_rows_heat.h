@@ -648,10 +648,12 @@ SF3D_HD void sf3d_row_heat_assemble(const SF3DView &v, uint32_t i, double dtHeat
 
 // one Jacobi row of the heat system; returns |dx| (the reference sweeps Gauss-Seidel in place with
 // the same row formula and an infinity norm, heat.cpp:664-685)
-SF3D_HD double sf3d_row_heat_jacobi(const SF3DView &v, uint32_t i, const double *__restrict__ xin, double *__restrict__ xout)
+SF3D_HD double sf3d_row_heat_jacobi(const SF3DView &v, uint32_t i, const double *__restrict__ xin, double *__restrict__ xout,
+                                    double *xnewOut = nullptr)
 {
     const size_t N = v.N;
     const double xold = xin[i];
+    if (xnewOut) *xnewOut = xold;
     if (i < v.Ns || v.hdiag[i] == 0.) { xout[i] = xold; return 0.; }
     const uint32_t m = v.meta[i];
     double xnew = v.b[i];
@@ -663,6 +665,7 @@ SF3D_HD double sf3d_row_heat_jacobi(const SF3DView &v, uint32_t i, const double 
         xnew -= A * xin[j];
     }
     xout[i] = xnew;
+    if (xnewOut) *xnewOut = xnew;
     return fabs(xnew - xold);
 }
 

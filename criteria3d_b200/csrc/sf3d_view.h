@@ -41,6 +41,13 @@ enum : uint32_t { BT_NONE = 0, BT_RUNOFF = 1, BT_FREE_DRAINAGE = 2, BT_FREE_LATE
 #define META_HAS_SLOT(m, s) (((m) >> (9 + (s))) & 1u)
 #define META_GHOST(m)     (((m) >> 19) & 1u)   // halo copy of a node owned by another rank (multi-GPU slabs)
 
+// 16-bit pattern id of a row (see kern_build_patterns): bits 0-14 index the pattern table; bit 15 marks rows the
+// interior loop of the multi-GPU sweep skips: ghost rows (id 0xFFFF, never swept) and boundary rows, which the sweep
+// computes FIRST so that their values travel to the neighbouring ranks while the interior rows are swept
+#define SF3D_PID_MASK     0x7FFFu
+#define SF3D_PID_SKIP     0x8000u
+#define SF3D_GHOST_PID    0xFFFFu
+
 // Matrix columns are stored in the reference's COLUMN order, which fixes the floating-point
 // summation order of the Jacobi row (cpusolver.cpp:352-374): column 0 = Up (slot 0),
 // columns 1..8 = Lateral 0..7 (slots 2..9), column 9 = Down (slot 1).
@@ -69,7 +76,8 @@ struct SolverParams {           // SolverParameters, types.h:291-315
 };
 
 // device control block: scalars produced by reductions and the on-device solver state
-enum : int { SOLVE_RUNNING = 0, SOLVE_CONVERGED = 1, SOLVE_DIVERGED = 2, SOLVE_MAXITER = 3, SOLVE_COURANT_FAIL = 4 };
+enum : int { SOLVE_RUNNING = 0, SOLVE_CONVERGED = 1, SOLVE_DIVERGED = 2, SOLVE_MAXITER = 3, SOLVE_COURANT_FAIL = 4,
+             SOLVE_COMM_ERROR = 5 };      // a row-slab peer did not answer an all-reduce: never a numerical event
 struct Ctrl {
     double courantMax;      // nodeGrid.CourantWater
     double storage;         // sum theta*V            (water.cpp:71-90)
@@ -82,7 +90,7 @@ struct Ctrl {
     int    status;          // SOLVE_*
     int    sweeps;          // sweeps executed in the current solve
     unsigned int ticket;    // last-block election counter
-    int    pad;
+    int    commError;       // multi-GPU: set when a mailbox all-reduce timed out; read_ctrl turns it into a DeviceError
     double red[4];          // multi-GPU: local reductions handed to the all-reduce before the rule is applied
 };
 

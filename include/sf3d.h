@@ -294,6 +294,14 @@ uint8_t sf3d_ext_jacobi_sweep(uint32_t n, uint32_t n_surface, const uint8_t *nco
                               const double *val, const double *b, const double *z, const double *x_in,
                               double *x_out, double *norm);
 
+/* Error of the most recent sf3d_compute_step / sf3d_compute_period, then cleared (SF3D_OK when the call
+ * succeeded).  The reference's computeStep returns the accepted time step and drops solver->run()'s error code
+ * (soilFluxes3D.cpp:1796); this is where a caller can still see it.  Product: SF3D_SOLVER_ERROR when a device
+ * or communication fault abandoned the step (e.g. a row-slab peer that did not answer an all-reduce within
+ * SF3D_MAILBOX_TIMEOUT_S) -- computeStep then returns the negative sentinel of getDoubleErrorValue instead
+ * of a time step and the state is undefined.  CPU libraries: always SF3D_OK. */
+uint8_t sf3d_ext_last_error(void);
+
 /* name/version of the implementation behind the ABI ("b200", "oracle", "reference") */
 const char *sf3d_ext_backend(void);
 
@@ -302,6 +310,11 @@ const char *sf3d_ext_backend(void);
  * cleanSF3D/initializeSF3D (cpusolver.cpp:105-134), so a second catchment in the same process
  * would otherwise start from the previous run's deltaTcurr.  Call before sf3d_initialize. */
 uint8_t sf3d_ext_reset_solver(void);
+
+/* Solver::setTimeStep (solver.h:77-86; as written there it ends up assigning the argument unclamped):
+ * the time step the next sf3d_compute_step starts from (deltaTcurr).  Together with sf3d_ext_set_field(TOTAL_POTENTIAL)
+ * and sf3d_initialize_balance it lets a harness replay the same steps from a saved state. */
+uint8_t sf3d_ext_set_time_step(double delta_t);
 
 /* product only: device selection and multi-GPU slab wiring.  The other
  * two libraries return SF3D_PARAMETER_ERROR. */
@@ -312,7 +325,9 @@ uint8_t sf3d_ext_set_device(int device);
  * catchment, then declares which local nodes are ghosts (recv lists) and which owned nodes the
  * neighbours need (send lists).  The library exchanges x on those lists after every Jacobi sweep
  * and all-reduces the residual, Courant and balance sums (NCCL over NVLink).
- * The 128-byte id is an ncclUniqueId: rank 0 creates it, the harness broadcasts it. */
+ * The 128-byte id is an ncclUniqueId: rank 0 creates it, the harness broadcasts it.  id == NULL: no NCCL
+ * communicator; the ranks then talk through peer memory only (sf3d_ext_ipc_* and sf3d_ext_mailbox_* must be wired
+ * before the first step), which also works for several ranks sharing one device (used by the tests). */
 uint8_t sf3d_ext_comm_unique_id(uint8_t id[128]);
 uint8_t sf3d_ext_comm_init(int rank, int world, const uint8_t id[128]);
 uint8_t sf3d_ext_comm_finalize(void);

@@ -282,6 +282,7 @@ uint8_t sf3d_ext_get_counters(sf3d_counters *out)
     return SF3D_OK;
 }
 uint8_t sf3d_ext_reset_counters(void) { std::memset(&g_cnt, 0, sizeof g_cnt); return SF3D_OK; }
+uint8_t sf3d_ext_last_error(void) { return SF3D_OK; }
 const char *sf3d_ext_backend(void) { return "reference"; }
 uint8_t sf3d_ext_set_device(int) { return SF3D_PARAMETER_ERROR; }
 uint8_t sf3d_ext_comm_unique_id(uint8_t id[128]) { (void)id; return SF3D_PARAMETER_ERROR; }
@@ -317,6 +318,13 @@ uint8_t sf3d_ext_jacobi_sweep(uint32_t n, uint32_t ns, const uint8_t *ncols, con
     g_cnt.sweeps = sweeps;
     sf::nodeGrid.z = saveZ; sf::nodeGrid.nrSurfaceNodes = saveNs;
     std::memcpy(x_out, vx.values, (size_t)n * sizeof(double));      /* the function swaps the two vectors */
+    return SF3D_OK;
+}
+uint8_t sf3d_ext_set_time_step(double delta_t)
+{
+    sf::SolverParametersPartial p;
+    p.deltaTcurr = delta_t;
+    sf::CPUSolverObject.updateParameters(p);
     return SF3D_OK;
 }
 uint8_t sf3d_ext_reset_solver(void)

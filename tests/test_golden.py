@@ -8,7 +8,7 @@ import pytest
 
 from criteria3d_b200 import SoilFluxes3D
 from oracle import ORACLE_LIB
-from scenarios import HEAT_SCENARIOS, SCENARIOS, compare
+from scenarios import HEAT_SCENARIOS, SCENARIOS, TOLERANCES, compare
 
 GOLDEN = Path(__file__).parent / "golden"
 
@@ -30,4 +30,4 @@ def test_oracle_matches_reference_golden(name):
 @pytest.mark.parametrize("name", sorted({**SCENARIOS, **HEAT_SCENARIOS}))
 def test_product_matches_reference_golden(product, name):
     fn = {**SCENARIOS, **HEAT_SCENARIOS}[name]
-    compare(fn(product), _load(name), exact=False)
+    compare(fn(product), _load(name), exact=False, **TOLERANCES.get(name, {}))

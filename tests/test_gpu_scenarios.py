@@ -3,7 +3,7 @@
 tests/test_gpu_parity.py."""
 import pytest
 
-from scenarios import HEAT_SCENARIOS, SCENARIOS, compare
+from scenarios import HEAT_SCENARIOS, SCENARIOS, TOLERANCES, compare
 
 pytestmark = pytest.mark.gpu
 
@@ -20,7 +20,7 @@ def test_heat_scenario(product, checker, name):
     """coupled heat (Jacobi on the GPU vs the reference's Gauss-Seidel: same fixed point)"""
     a = HEAT_SCENARIOS[name](product)
     b = HEAT_SCENARIOS[name](checker)
-    compare(a, b, exact=False)
+    compare(a, b, exact=False, **TOLERANCES.get(name, {}))
 
 
 def test_heat_coupled_medium(product, checker):
