@@ -68,7 +68,8 @@ void k_update_conductance(const SF3DView &v);
 void k_save_water_fluxes(const SF3DView &v, double dtHeat, double dtWater);
 void k_reset_water_fluxes(const SF3DView &v);
 void k_boundary_heat(const SF3DView &v, double maxTimeStep);
-void k_heat_begin(const SF3DView &v, double dtHeat, double dtWater);
+void k_heat_begin(const SF3DView &v, double dtHeat, double dtWater, bool coeffsAreCurrent);   // coeffsAreCurrent: the per-node
+                                    // coefficients stored by k_save_water_fluxes were computed with the same (dtHeat, T): not recomputed
 void k_heat_assemble(const SF3DView &v, double dtHeat, double dtWater);
 void k_heat_jacobi(const SF3DView &v, const double *xin, double *xout, int maxIter, double tol);
 void k_heat_post(const SF3DView &v, const double *x, double dtHeat, double dtWater, int mode);

@@ -56,7 +56,8 @@ double Engine::computeStep(double maxTimeStep)
     if (computeHeat)
     {
         double dtHeat = dtWater;
-        k_save_water_fluxes(v, dtHeat, dtWater);
+        k_save_water_fluxes(v, dtHeat, dtWater);            // stores the per-node coefficients for (dtHeat, T) first
+        heatCoeffsCurrent = true; heatCoeffsDt = dtHeat;
         double dtHeatSum = 0.;
         while (dtHeatSum < dtWater)
         {
@@ -107,7 +108,8 @@ void Engine::runHeat(double maxTimeStep, double dtWater)
 // cap so that it reaches the tolerance whenever Gauss-Seidel does.
 bool Engine::heatLoop(double timeStepHeat, double timeStepWater)
 {
-    k_heat_begin(v, timeStepHeat, timeStepWater);       // reset heat fluxes ; x = T ; oldT = T ; C
+    k_heat_begin(v, timeStepHeat, timeStepWater, heatCoeffsCurrent && heatCoeffsDt == timeStepHeat);   // reset heat fluxes ; x = T ; oldT = T ; C
+    heatCoeffsCurrent = false;                          // the solve below changes T
     k_heat_assemble(v, timeStepHeat, timeStepWater);
 
     const int refCap = (int)calcCurrentMaxIterationNumber((int)p->maxApproximationsNumber - 1);

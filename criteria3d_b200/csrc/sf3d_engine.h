@@ -28,6 +28,10 @@ struct Engine {
     int lastSweeps = 6;                     // sweeps of the previous solve (launch batching hint)
     bool computeWater = true;
     bool computeHeat = false;
+    // per-node heat coefficients (kern_heat_coeffs) currently stored for this heat sub-step length, with the current
+    // temperatures: the first heatLoop after the flux snapshot does not recompute them
+    bool heatCoeffsCurrent = false;
+    double heatCoeffsDt = 0.;
 
     double *xbuf(int k) const { return k ? v.x1 : v.x0; }
 

@@ -920,7 +920,7 @@ __global__ void kern_rule_heat_jacobi(Ctrl *c, int maxIter, double tol)
     if (c->status != SOLVE_RUNNING) return;
     rule_heat_jacobi(c, c->red[0], maxIter, tol);
 }
-__global__ void __launch_bounds__(SF3D_BLOCK) kern_heat_jacobi(SF3DView v, const double *__restrict__ xin,
+__global__ void __launch_bounds__(SF3D_BLOCK, SF3D_JACOBI_BLOCKS) kern_heat_jacobi(SF3DView v, const double *__restrict__ xin,
                                                                double *__restrict__ xout, int maxIter, double tol)
 {
     if (v.ctrl->status != SOLVE_RUNNING) return;
@@ -928,7 +928,7 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_heat_jacobi(SF3DView v, const
     double norm = 0.;
     for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
     {
-        if (v.world > 1 && META_GHOST(v.meta[i])) continue;
+        if (v.world > 1 && (v.pid ? (v.pid[i] == SF3D_GHOST_PID) : (META_GHOST(v.meta[i]) != 0))) continue;
         const double d = sf3d_row_heat_jacobi(v, i, xin, xout);
         norm = (norm < d) ? d : norm;
     }
@@ -1470,11 +1470,11 @@ void k_boundary_heat(const SF3DView &v, double maxTimeStep)
     kern_boundary_heat<<<GRID(v.N)>>>(v, maxTimeStep, cm); LAUNCH_CHECK();
     if (v.world > 1 && !cm.mine) { comm_allreduce(v.ctrl->red, 1, true, v.ctrl); kern_rule_heat_courant<<<1, 1, 0, g_stream>>>(v.ctrl); LAUNCH_CHECK(); }
 }
-void k_heat_begin(const SF3DView &v, double dtHeat, double dtWater)
+void k_heat_begin(const SF3DView &v, double dtHeat, double dtWater, bool coeffsAreCurrent)
 {
     ProfScope ps(SF3D_K_HEAT_COEFFS);
     kern_heat_begin<<<GRID(v.N)>>>(v, dtHeat, dtWater); LAUNCH_CHECK();
-    kern_heat_coeffs<<<GRID(v.N)>>>(v, dtHeat, dtWater); LAUNCH_CHECK();
+    if (!coeffsAreCurrent) { kern_heat_coeffs<<<GRID(v.N)>>>(v, dtHeat, dtWater); LAUNCH_CHECK(); }
 }
 void k_heat_assemble(const SF3DView &v, double dtHeat, double dtWater)
 { ProfScope ps(SF3D_K_HEAT_ASSEMBLE); kern_heat_assemble<<<GRID(v.N)>>>(v, dtHeat, dtWater); LAUNCH_CHECK(); }

@@ -20,7 +20,7 @@
 // kernels (Se, Mualem K) gain ~40 %.  -DSF3D_REFERENCE_ROUNDING keeps pow().
 SF3D_HD double sf3d_pow(double x, double y)
 {
-#if defined(__CUDA_ARCH__) && !defined(SF3D_REFERENCE_ROUNDING)
+#ifdef SF3D_DEVICE_MATH
     if (!(x > 0.)) return pow(x, y);            // zero / negative / NaN base: the library's special cases
     return exp(y * log(x));
 #else
@@ -386,8 +386,9 @@ SF3D_HD double sf3d_runoff(const SF3DView &v, uint32_t i, uint32_t j, int approx
     return Kij;
 }
 
-SF3D_HD double sf3d_heat_thermal_invariant(const SF3DView &v, uint32_t i, int slot, double tli, double tvi, double tmi,
-                                          double tlj, double tvj, double tmj);   // water.cpp:329-340
+SF3D_HD double sf3d_heat_thermal_invariant(const SF3DView &v, uint32_t i, int slot, const SF3DPair tli, const SF3DPair tvi, double tmi,
+                                          const SF3DPair tlj, const SF3DPair tvj, double tmj);   // water.cpp:329-340
+SF3D_HD SF3DPair h_pair_load(const double *arr, uint32_t i);
 
 // ==========================================================================================
 // assembly of one row: CPUSolver::computeLinearSystemElement + computeDiagonalElement +
@@ -446,6 +447,9 @@ SF3D_HD uint32_t sf3d_col_index(const SF3DView &v, const int32_t *__restrict__ o
     return off ? (uint32_t)((int64_t)i + off[c]) : v.mcol[(size_t)c * v.N + i];
 }
 
+#ifndef SF3D_HEAT_ASSEMBLE_GROUP
+#define SF3D_HEAT_ASSEMBLE_GROUP 2      // must divide 10
+#endif
 // soil row: every link is a redistribution except an Up link to a surface node (infiltration).
 // The ten neighbour conductivities are gathered first (independent loads), then the means.
 template <bool HEAT>
@@ -457,40 +461,46 @@ SF3D_HD double sf3d_row_assemble_soil(const SF3DView &v, uint32_t i, double dt, 
     const double ki = v.K[i];
     const int32_t *off = sf3d_row_pattern(v, i);
     double sum = 0., invariant = 0.;
-    double tli = 0., tvi = 0., tmi = 0.;
-    if (HEAT) { tli = v.hTLK[i]; tmi = v.hTm[i]; if (v.computeHeatVapor) tvi = v.hTVK[i]; }
+    SF3DPair tli = {0., 0.}, tvi = {0., 0.};
+    double tmi = 0.;
+    if (HEAT) { tli = h_pair_load(v.hTLK, i); tmi = v.hTm[i]; if (v.computeHeatVapor) tvi = h_pair_load(v.hTVK, i); }
+    // links are handled in groups: all gathers of a group are issued before its arithmetic (independent loads in
+    // flight).  Water only: two groups of five; with the heat coupling every link carries five more operands
+    // (thermal liquid / vapour conductivity pairs, mean temperature), so the groups are shorter to stay in registers
+    constexpr int G = HEAT ? SF3D_HEAT_ASSEMBLE_GROUP : 5;
     #pragma unroll
-    for (int half = 0; half < 2; ++half)
+    for (int base = 0; base < SF3D_NLINK; base += G)
     {
-        uint32_t j[5];
-        double g[5], kj[5];
-        double tl[5], tv[5], tm[5];
+        uint32_t j[G];
+        double g[G], kj[G];
+        SF3DPair tl[G], tv[G];
+        double tm[G];
         #pragma unroll
-        for (int q = 0; q < 5; ++q)
+        for (int q = 0; q < G; ++q)
         {
-            const int c = half * 5 + q;
+            const int c = base + q;
             j[q] = sf3d_col_index(v, off, i, c);
             g[q] = SF3D_LDS(v.lgeom + (size_t)c * N + i);
         }
         #pragma unroll
-        for (int q = 0; q < 5; ++q) kj[q] = v.K[j[q]];
+        for (int q = 0; q < G; ++q) kj[q] = v.K[j[q]];
         if (HEAT)
         {
             #pragma unroll
-            for (int q = 0; q < 5; ++q)
+            for (int q = 0; q < G; ++q)
             {
-                tl[q] = v.hTLK[j[q]]; tm[q] = v.hTm[j[q]];
-                tv[q] = v.computeHeatVapor ? v.hTVK[j[q]] : 0.;
+                tl[q] = h_pair_load(v.hTLK, j[q]); tm[q] = v.hTm[j[q]];
+                if (v.computeHeatVapor) tv[q] = h_pair_load(v.hTVK, j[q]); else { tv[q].v = 0.; tv[q].l = 0.; }
             }
         }
         #pragma unroll
-        for (int q = 0; q < 5; ++q)
+        for (int q = 0; q < G; ++q)
         {
-            const int c = half * 5 + q;
+            const int c = base + q;
             const int slot = sf3d_slot_of_col(c);
             double kc;
-            if (c == 0 && j[0] < v.Ns)                    // first soil layer: link to the surface node above
-                kc = sf3d_infiltration(v, j[0], i, dt, v.larea[i], g[0]);
+            if (c == 0 && j[q] < v.Ns)                    // first soil layer: link to the surface node above
+                kc = sf3d_infiltration(v, j[q], i, dt, v.larea[i], g[q]);
             else
             {
 #ifdef SF3D_REFERENCE_ROUNDING

@@ -34,7 +34,7 @@ constexpr int kHeatLinkUnroll = SF3D_HEAT_LINK_UNROLL;
 
 // pow() with the small integer exponents heat.cpp passes: the product multiplies, the reference-rounding
 // build calls the library like the reference does
-#if defined(__CUDA_ARCH__) && !defined(SF3D_REFERENCE_ROUNDING)
+#ifdef SF3D_DEVICE_MATH
 SF3D_HD double h_pow1(double x) { return x; }
 SF3D_HD double h_pow2(double x) { return x * x; }
 SF3D_HD double h_pow3(double x) { return x * x * x; }
@@ -205,6 +205,43 @@ SF3D_HD double h_distance3d(const SF3DView &v, uint32_t i, uint32_t j)          
     double n = 0; n += dx * dx; n += dy * dy; n += dz * dz;
     return sqrt(n);
 }
+// ---- link operands and link factors ------------------------------------------------------------
+// Every heat / vapour flux of a link is  coefficient x difference / nodeDistance3D x interfaceArea  with a
+// logarithmic mean (Math::computeMean, default type) of a per-node coefficient.  The reference-rounding build
+// evaluates exactly that.  Device math (sf3d_view.h) keeps interfaceArea / nodeDistance3D per link (static, one
+// load, no division) and every per-node coefficient together with its logarithm (SF3DPair).
+SF3D_HD double h_logmean_pre(const SF3DPair a, const SF3DPair b)
+{
+    // (a - b) / (ln a - ln b).  Nearly equal operands: the series of the logarithmic mean around the arithmetic
+    // mean m, x = (a - b) / (a + b):  m (1 - x^2 / 3 - ...), exact to 1e-17 for |x| <= 5e-5, where the difference of
+    // two stored logarithms would have lost its digits.  A zero operand (saturated node: no vapour diffusion)
+    // gives 0 like the reference's (0 - b) / ln(0 / b).
+    if (a.v == b.v) return a.v;
+    const double d = a.v - b.v, s = a.v + b.v;
+    const bool close = fabs(d) <= 1e-4 * fabs(s);
+    const double q = d / (close ? s : (a.l - b.l));
+    return close ? 0.5 * s * (1. - q * q * (1. / 3.)) : q;
+}
+#ifdef SF3D_DEVICE_MATH
+SF3D_HD void h_pair_store(double *arr, uint32_t i, double value)
+{ SF3DPair p; p.v = value; p.l = log(value); reinterpret_cast<SF3DPair *>(arr)[i] = p; }
+SF3D_HD SF3DPair h_pair_load(const double *arr, uint32_t i) { return reinterpret_cast<const SF3DPair *>(arr)[i]; }
+SF3D_HD double h_pair_value(const double *arr, uint32_t i) { return reinterpret_cast<const SF3DPair *>(arr)[i].v; }
+SF3D_HD double h_pair_mean(const SF3DPair a, const SF3DPair b) { return h_logmean_pre(a, b); }
+SF3D_HD double h_link_zeta(const SF3DView &v, uint32_t i, int slot) { return SF3D_LDS(v.ldist3 + (size_t)slot * v.N + i); }
+SF3D_HD double h_link_flux(const SF3DView &v, uint32_t i, int slot, double density) { return density * h_link_zeta(v, i, slot); }
+SF3D_HD double h_link_store_geometry(double area, double distance3d) { return area / distance3d; }
+#else
+SF3D_HD void h_pair_store(double *arr, uint32_t i, double value) { arr[i] = value; }
+SF3D_HD SF3DPair h_pair_load(const double *arr, uint32_t i) { SF3DPair p; p.v = arr[i]; p.l = 0.; return p; }
+SF3D_HD double h_pair_value(const double *arr, uint32_t i) { return arr[i]; }
+SF3D_HD double h_pair_mean(const SF3DPair a, const SF3DPair b) { return sf3d_mean(a.v, b.v, 2); }
+SF3D_HD double h_link_zeta(const SF3DView &v, uint32_t i, int slot)       // Heat::conduction: area / distance (heat.cpp:647)
+{ return v.larea[(size_t)slot * v.N + i] / v.ldist3[(size_t)slot * v.N + i]; }
+SF3D_HD double h_link_flux(const SF3DView &v, uint32_t i, int slot, double density)    // ... / distance * area, as written in heat.cpp
+{ return density / v.ldist3[(size_t)slot * v.N + i] * v.larea[(size_t)slot * v.N + i]; }
+SF3D_HD double h_link_store_geometry(double, double distance3d) { return distance3d; }
+#endif
 // static heat geometry, filled once per topology: ldist3[slot][i] and hPress[i]
 SF3D_HD void sf3d_row_heat_geometry(const SF3DView &v, uint32_t i)
 {
@@ -212,9 +249,28 @@ SF3D_HD void sf3d_row_heat_geometry(const SF3DView &v, uint32_t i)
     const uint32_t m = v.meta[i];
     v.hPress[i] = h_pressure_from_altitude(v.z[i]);
     for (int slot = 0; slot < SF3D_NLINK; ++slot)
-        v.ldist3[(size_t)slot * N + i] = META_HAS_SLOT(m, slot) ? h_distance3d(v, i, v.lidx[(size_t)slot * N + i]) : 1.;
+        v.ldist3[(size_t)slot * N + i] = META_HAS_SLOT(m, slot)
+            ? h_link_store_geometry(v.larea[(size_t)slot * N + i], h_distance3d(v, i, v.lidx[(size_t)slot * N + i])) : 1.;
 }
-SF3D_HD double h_link_distance3d(const SF3DView &v, uint32_t i, int slot) { return SF3D_LDS(v.ldist3 + (size_t)slot * v.N + i); }
+
+// getNodeH_fromTimeSteps of a linked node and its sub-step averaged matric head: stored per node by
+// sf3d_row_heat_coeffs under device math (same expressions), evaluated on the spot otherwise
+SF3D_HD double h_Hs(const SF3DView &v, uint32_t j, double dtHeat, double dtWater)
+{
+#ifdef SF3D_DEVICE_MATH
+    (void)dtHeat; (void)dtWater; return v.hHs[j];
+#else
+    return h_H_from_steps(v, j, dtHeat, dtWater);
+#endif
+}
+SF3D_HD double h_psi_avg(const SF3DView &v, uint32_t j, double dtHeat, double dtWater)
+{
+#ifdef SF3D_DEVICE_MATH
+    (void)dtHeat; (void)dtWater; return v.hPsiAvg[j];
+#else
+    return (h_H_from_steps(v, j, dtHeat, dtWater) + v.oldH[j]) * 0.5 - v.z[j];
+#endif
+}
 
 // ---- water-side hooks --------------------------------------------------------------------------
 // computeNodeK's vapour term (soilPhysics.cpp:168-169) from the node's current state (bulk potential setter)
@@ -240,7 +296,7 @@ SF3D_HD double sf3d_heat_node_water(const SF3DView &v, uint32_t i, const SoilRec
         const double theta = (h >= 0.) ? s.thetaS : sf3d_theta_from_se(s, Se);
         const HeatNodeCtx c = h_node_ctx(s, T, h, theta);
         K += h_ivk(c) * (HC_GRAVITY / HC_WATER_DENSITY);
-        v.hTVK[i] = h_tvk(s, c, v.hPress[i]);
+        h_pair_store(v.hTVK, i, h_tvk(s, c, v.hPress[i]));
         if (dThetadH)
         {
             const double dThetaVdPsi = (c.svc * c.rh / HC_WATER_DENSITY) * ((s.thetaS - theta) * HC_MH2O / (HC_R_GAS * T) - *dThetadH / HC_GRAVITY);
@@ -248,7 +304,7 @@ SF3D_HD double sf3d_heat_node_water(const SF3DView &v, uint32_t i, const SoilRec
         }
     }
     v.hTm[i] = T;
-    v.hTLK[i] = h_thermal_liquid_conductivity(T - HC_ZEROCELSIUS, h, K);
+    h_pair_store(v.hTLK, i, h_thermal_liquid_conductivity(T - HC_ZEROCELSIUS, h, K));
     return K;
 }
 
@@ -256,55 +312,56 @@ SF3D_HD double sf3d_heat_node_water(const SF3DView &v, uint32_t i, const SoilRec
 // heat sub-step): stored by sf3d_row_heat_coeffs before the flux snapshot and before every heat assembly
 SF3D_HD void sf3d_row_heat_coeffs(const SF3DView &v, uint32_t i, double dtHeat, double dtWater)
 {
+    const double Hs = h_H_from_steps(v, i, dtHeat, dtWater);
+    const double avgH = (Hs + v.oldH[i]) * 0.5 - v.z[i];
+#ifdef SF3D_DEVICE_MATH
+    v.hHs[i] = Hs; v.hPsiAvg[i] = avgH;         // surface nodes too: the water flux snapshot reads the head of both ends
+#endif
     if (i < v.Ns) return;
-    const double avgH = (h_H_from_steps(v, i, dtHeat, dtWater) + v.oldH[i]) * 0.5 - v.z[i];
     const double T = v.T[i];
     const SoilRec &s = h_soil(v, i);
     const HeatNodeCtx c = h_node_ctx(s, T, avgH, h_theta(v, i, avgH));
     const double tvk = h_tvk(s, c, v.hPress[i]);
-    v.hCond[i] = h_soil_heat_conductivity(s, c, tvk);
-    v.hIVK[i] = h_ivk(c);
-    v.hTVK[i] = tvk;
+    h_pair_store(v.hCond, i, h_soil_heat_conductivity(s, c, tvk));
+    h_pair_store(v.hIVK, i, h_ivk(c));
+    h_pair_store(v.hTVK, i, tvk);
     // computeThermalLiquidFlux, processType::Heat (heat.cpp:458-500): its head is the sub-step average only
     // when the heat step differs from the water step
     const double liquidH = (dtHeat != dtWater) ? avgH : (v.H[i] + v.oldH[i]) * 0.5 - v.z[i];
-    v.hTLKh[i] = h_thermal_liquid_conductivity(T - HC_ZEROCELSIUS, liquidH, v.K[i]);
+    h_pair_store(v.hTLKh, i, h_thermal_liquid_conductivity(T - HC_ZEROCELSIUS, liquidH, v.K[i]));
 }
 
 // computeThermalLiquidFlux / computeThermalVaporFlux (heat.cpp:458-553), processType::Heat branch: node
 // temperatures, conductivities stored per node by sf3d_row_heat_coeffs with exactly these arguments
 SF3D_HD double h_thermal_liquid_flux_heat(const SF3DView &v, uint32_t i, int slot, uint32_t j)
 {
-    const double avg = sf3d_mean(v.hTLKh[i], v.hTLKh[j], 2);     // computeMean default = Logarithmic
-    const double density = avg * (v.T[j] - v.T[i]) / h_link_distance3d(v, i, slot);
-    return density * v.larea[(size_t)slot * v.N + i];
+    const double avg = h_pair_mean(h_pair_load(v.hTLKh, i), h_pair_load(v.hTLKh, j));     // computeMean default = Logarithmic
+    return h_link_flux(v, i, slot, avg * (v.T[j] - v.T[i]));
 }
 SF3D_HD double h_thermal_vapor_flux_heat(const SF3DView &v, uint32_t i, int slot, uint32_t j, double dtHeat, double dtWater, bool usePre)
 {
-    double a, b;
-    if (usePre) { a = v.hTVK[i]; b = v.hTVK[j]; }
+    double avg;
+    if (usePre) avg = h_pair_mean(h_pair_load(v.hTVK, i), h_pair_load(v.hTVK, j));
     else
     {
-        const double srcH = (h_H_from_steps(v, i, dtHeat, dtWater) + v.oldH[i]) * 0.5 - v.z[i];
-        const double dstH = (h_H_from_steps(v, j, dtHeat, dtWater) + v.oldH[j]) * 0.5 - v.z[j];
-        a = h_thermal_vapor_conductivity(v, i, v.T[i], srcH);
-        b = h_thermal_vapor_conductivity(v, j, v.T[j], dstH);
+        // after the heat solve (saveNodeHeatFluxes): the conductivities of the NEW temperatures, evaluated on the spot
+        const double srcH = h_psi_avg(v, i, dtHeat, dtWater);
+        const double dstH = h_psi_avg(v, j, dtHeat, dtWater);
+        const double a = h_thermal_vapor_conductivity(v, i, v.T[i], srcH);
+        const double b = h_thermal_vapor_conductivity(v, j, v.T[j], dstH);
+        avg = sf3d_mean(a, b, 2);
     }
-    const double avg = sf3d_mean(a, b, 2);
-    const double density = avg * (v.T[j] - v.T[i]) / h_link_distance3d(v, i, slot);
-    return density * v.larea[(size_t)slot * v.N + i];
+    return h_link_flux(v, i, slot, avg * (v.T[j] - v.T[i]));
 }
 // water.cpp:329-340: thermal liquid (+ vapour / rho_w) flux added to the row's invariant fluxes
 // (processType::Water branch).  tl / tv / tm: thermal liquid conductivity, thermal vapour conductivity
 // and mean temperature of the two ends, stored by sf3d_heat_node_water.
-SF3D_HD double sf3d_heat_thermal_invariant(const SF3DView &v, uint32_t i, int slot, double tli, double tvi, double tmi,
-                                          double tlj, double tvj, double tmj)
+SF3D_HD double sf3d_heat_thermal_invariant(const SF3DView &v, uint32_t i, int slot, const SF3DPair tli, const SF3DPair tvi, double tmi,
+                                          const SF3DPair tlj, const SF3DPair tvj, double tmj)
 {
-    const double d3 = h_link_distance3d(v, i, slot);
-    const double area = SF3D_LDS(v.larea + (size_t)slot * v.N + i);
     const double dT = tmj - tmi;
-    double f = (sf3d_mean(tli, tlj, 2) * dT / d3) * area;
-    if (v.computeHeatVapor) f += ((sf3d_mean(tvi, tvj, 2) * dT / d3) * area) / HC_WATER_DENSITY;
+    double f = h_link_flux(v, i, slot, h_pair_mean(tli, tlj) * dT);
+    if (v.computeHeatVapor) f += h_link_flux(v, i, slot, h_pair_mean(tvi, tvj) * dT) / HC_WATER_DENSITY;
     return f;
 }
 
@@ -419,14 +476,13 @@ SF3D_HD void sf3d_row_update_conductance(const SF3DView &v, uint32_t i)
 // ==========================================================================================
 SF3D_HD double h_isothermal_vapor_flux(const SF3DView &v, uint32_t i, int slot, uint32_t j, double dtHeat, double dtWater)   // :561-582
 {
-    const double srcH = (h_H_from_steps(v, i, dtHeat, dtWater) + v.oldH[i]) * 0.5 - v.z[i];
-    const double dstH = (h_H_from_steps(v, j, dtHeat, dtWater) + v.oldH[j]) * 0.5 - v.z[j];
-    const double a = v.hIVK[i];          // = computeNodeIsothermalVaporConductivity(i, T[i], srcH), see sf3d_row_heat_coeffs
-    const double b = v.hIVK[j];
-    const double avg = sf3d_mean(a, b, 2);
+    const double srcH = h_psi_avg(v, i, dtHeat, dtWater);
+    const double dstH = h_psi_avg(v, j, dtHeat, dtWater);
+    // operands = computeNodeIsothermalVaporConductivity(node, T[node], its averaged head), see sf3d_row_heat_coeffs
+    const double avg = h_pair_mean(h_pair_load(v.hIVK, i), h_pair_load(v.hIVK, j));
     const double srcPsi = srcH * HC_GRAVITY, dstPsi = dstH * HC_GRAVITY;
     const double deltaPsi = dstPsi - srcPsi;
-    return avg * deltaPsi / h_link_distance3d(v, i, slot) * v.larea[(size_t)slot * v.N + i];
+    return h_link_flux(v, i, slot, avg * deltaPsi);
 }
 SF3D_HD void sf3d_row_save_water_fluxes(const SF3DView &v, uint32_t i, double dtHeat, double dtWater)
 {
@@ -438,8 +494,8 @@ SF3D_HD void sf3d_row_save_water_fluxes(const SF3DView &v, uint32_t i, double dt
         if (!META_HAS_SLOT(m, slot)) continue;
         const size_t li = (size_t)slot * N + i;
         const uint32_t j = v.lidx[li];
-        const double srcAvgH = h_H_from_steps(v, i, dtHeat, dtWater);
-        const double dstAvgH = h_H_from_steps(v, j, dtHeat, dtWater);
+        const double srcAvgH = h_Hs(v, i, dtHeat, dtWater);
+        const double dstAvgH = h_Hs(v, j, dtHeat, dtWater);
         const double A = v.mval[(size_t)sf3d_col_of_slot(slot) * N + i];      // normalised entry x 1.0 (Q1); 0 if not stored (Q2)
         const double isoLiquid = A * (srcAvgH - dstAvgH);
         const bool deep = !(i < v.Ns) && !(j < v.Ns);
@@ -555,11 +611,10 @@ SF3D_HD void h_save_specific_flux(const SF3DView &v, uint32_t i, int slot, int t
 // Heat::conduction (heat.cpp:643-661)
 SF3D_HD double h_conduction(const SF3DView &v, uint32_t i, int slot, uint32_t j, double dtHeat, double dtWater)
 {
-    const double zeta = v.larea[(size_t)slot * v.N + i] / h_link_distance3d(v, i, slot);
+    const double zeta = h_link_zeta(v, i, slot);
     (void)dtHeat; (void)dtWater;
-    const double nodeK = v.hCond[i];     // = computeNodeHeatSoilConductivity(i, T[i], avgH_i), see sf3d_row_heat_coeffs
-    const double linkK = v.hCond[j];
-    return zeta * sf3d_mean(nodeK, linkK, 2);
+    // operands = computeNodeHeatSoilConductivity(node, T[node], its averaged head), see sf3d_row_heat_coeffs
+    return zeta * h_pair_mean(h_pair_load(v.hCond, i), h_pair_load(v.hCond, j));
 }
 // computeAdvectiveFlux (heat.cpp:606-621)
 SF3D_HD double h_advective_flux(const SF3DView &v, uint32_t i, int slot, uint32_t j)
@@ -590,11 +645,20 @@ SF3D_HD void sf3d_row_heat_assemble(const SF3DView &v, uint32_t i, double dtHeat
     const double nodeH = h_H_from_steps(v, i, dtHeat, dtWater);
     const double oldPsi = v.oldH[i] - v.z[i];
     const SoilRec &s = h_soil(v, i);
-    const double dTheta = sf3d_theta_from_signed_psi(s, v.wrcModel, nodeH - v.z[i]) - sf3d_theta_from_signed_psi(s, v.wrcModel, oldPsi);
+    // the two water contents are evaluated once and shared by the liquid and the vapour terms (the reference
+    // evaluates computeNodeTheta_fromSignedPsi with the same arguments inside computeNodeVaporThetaV again).
+    // theta(oldPsi): Se of the step's starting head is the stored SeOld, the value computeNodeSe_fromPsi returns
+    // for |oldPsi| (same function, same argument: sf3d_row_begin_try)
+    const double thetaNew = sf3d_theta_from_signed_psi(s, v.wrcModel, nodeH - v.z[i]);
+    const double thetaOld = (oldPsi >= 0.) ? s.thetaS : sf3d_theta_from_se(s, v.SeOld[i]);
+    const double dTheta = thetaNew - thetaOld;
     double heatCapacity = dTheta * HC_HEAT_CAPACITY_WATER * nodeT;
     if (v.computeHeatVapor)
     {
-        const double dThetaV = h_vapor_theta_v(v, i, nodeH - v.z[i], nodeT) - h_vapor_theta_v(v, i, oldPsi, v.oldT[i]);
+        // computeNodeVaporThetaV (heat.cpp:868-875) with the water contents above
+        const double vNew = h_vapor_from_psi_temp(nodeH - v.z[i], nodeT) / HC_WATER_DENSITY * (s.thetaS - thetaNew);
+        const double vOld = h_vapor_from_psi_temp(oldPsi, v.oldT[i]) / HC_WATER_DENSITY * (s.thetaS - thetaOld);
+        const double dThetaV = vNew - vOld;
         heatCapacity += dThetaV * HC_HEAT_CAPACITY_AIR * nodeT;
         heatCapacity += dThetaV * h_latent_vaporization(nodeT - HC_ZEROCELSIUS) * HC_WATER_DENSITY;
     }
@@ -647,22 +711,35 @@ SF3D_HD void sf3d_row_heat_assemble(const SF3DView &v, uint32_t i, double dtHeat
 }
 
 // one Jacobi row of the heat system; returns |dx| (the reference sweeps Gauss-Seidel in place with
-// the same row formula and an infinity norm, heat.cpp:664-685)
+// the same row formula and an infinity norm, heat.cpp:664-685).  Entries are stored and
+// summed in SLOT order (= the reference's column order Up, Down, Lateral 0..7); the linked node of a slot comes
+// from the row's link pattern like in the water sweep (absent links and links to surface nodes hold a zero
+// entry pointing at the row itself / at a finite x), so no index array and no meta word are read.
 SF3D_HD double sf3d_row_heat_jacobi(const SF3DView &v, uint32_t i, const double *__restrict__ xin, double *__restrict__ xout,
                                     double *xnewOut = nullptr)
 {
     const size_t N = v.N;
     const double xold = xin[i];
     if (xnewOut) *xnewOut = xold;
-    if (i < v.Ns || v.hdiag[i] == 0.) { xout[i] = xold; return 0.; }
-    const uint32_t m = v.meta[i];
-    double xnew = v.b[i];
+    if (i < v.Ns || SF3D_LDS(v.hdiag + i) == 0.) { xout[i] = xold; return 0.; }
+    uint32_t j[SF3D_NLINK];
+    if (v.pid) sf3d_row_cols(v, i, j);          // j[c]: COLUMN order (Up, Lateral 0..7, Down)
+    else
+    {
+        const uint32_t m = v.meta[i];
+        #pragma unroll
+        for (int c = 0; c < SF3D_NLINK; ++c)
+        {
+            const int slot = sf3d_slot_of_col(c);
+            j[c] = META_HAS_SLOT(m, slot) ? v.lidx[(size_t)slot * N + i] : i;
+        }
+    }
+    double xnew = SF3D_LDS(v.b + i);
     #pragma unroll
     for (int slot = 0; slot < SF3D_NLINK; ++slot)
     {
-        const double A = v.mval[(size_t)slot * N + i];
-        const uint32_t j = META_HAS_SLOT(m, slot) ? v.lidx[(size_t)slot * N + i] : i;
-        xnew -= A * xin[j];
+        const double A = SF3D_LDS(v.mval + (size_t)slot * N + i);
+        xnew -= A * xin[j[sf3d_col_of_slot(slot)]];
     }
     xout[i] = xnew;
     if (xnewOut) *xnewOut = xnew;

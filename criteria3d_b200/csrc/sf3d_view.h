@@ -24,6 +24,22 @@
 #define SF3D_LDS(p) (*(p))
 #endif
 
+// SF3D_DEVICE_MATH selects the arithmetic variants of the product's device code (powers as exp(y log x), small
+// integer powers as multiplications, per-node logarithms of the link means): a few ulp from the reference's
+// expressions, far inside the stated tolerances.  -DSF3D_REFERENCE_ROUNDING keeps the reference's expressions
+// everywhere; -DSF3D_HOST_DEVICE_MATH compiles the device variants for the host as well (development builds that
+// run the row functions on the CPU to check tolerances without a GPU).
+#if (defined(__CUDA_ARCH__) || defined(SF3D_HOST_DEVICE_MATH)) && !defined(SF3D_REFERENCE_ROUNDING)
+#define SF3D_DEVICE_MATH 1
+#endif
+
+// A per-node operand of the logarithmic link means of the heat closures (thermal liquid / vapour conductivity,
+// isothermal vapour conductivity, soil heat conductivity).  Device math keeps the value TOGETHER with its natural
+// logarithm (16 bytes, one vector load per gather): mean(a, b) = (a - b) / (ln a - ln b) then costs one division per
+// link instead of two divisions and a logarithm; the reference-rounding build stores the value only and evaluates
+// Math::computeMean as written.  The arrays are allocated with two doubles per node in both builds.
+struct alignas(16) SF3DPair { double v, l; };
+
 #define SF3D_NLINK 10           // maxTotalLink, types.h:25
 #define SF3D_NODATA (-9999.0)   // commonConstants.h:31
 
@@ -140,12 +156,14 @@ struct SF3DView {
     double *hdiag;                  // heat matrix diagonal (kept, cpusolver.cpp:561-567)
     // per-node coefficients the reference re-evaluates for both ends of every link (same arguments, same
     // value): thermal / isothermal vapour conductivity and soil heat conductivity, computed once per node
-    double *hTVK, *hIVK, *hCond;
+    double *hTVK, *hIVK, *hCond;    // (each of these five link operands: SF3DPair per node under device math, see above)
     // water-side coupling, stored by the node phase: mean temperature and thermal liquid conductivity
     // (mean T, current psi); heat side: thermal liquid conductivity (T, sub-step averaged psi)
     double *hTm, *hTLK, *hTLKh;
+    double *hHs, *hPsiAvg;          // heat side, per sub-step: getNodeH_fromTimeSteps and the sub-step averaged matric head
     double *hPress;                 // static: pressureFromAltitude(z), heat.cpp:1117
-    double *ldist3;                 // static: nodeDistance3D per link, slot-major (soilPhysics.cpp:331-335)
+    double *ldist3;                 // static per link, slot-major: nodeDistance3D (soilPhysics.cpp:331-335); device math
+                                    // stores interfaceArea / nodeDistance3D instead (every use is flux density x area / distance)
     // control / reduction scratch
     Ctrl *ctrl;
     double *partA, *partB;          // per-block partials
