@@ -71,7 +71,7 @@ struct State {
     Mirror<double> lfluxes;               // [type][slot][node]; 1 type (HeatTotal) unless save mode All (9)
     int hfTypesAllocated = 0;
     double *hFlux = nullptr, *lwFlux = nullptr, *lvFlux = nullptr, *hdiag = nullptr, *hTVK = nullptr, *hIVK = nullptr, *hCond = nullptr,
-           *hTm = nullptr, *hTLK = nullptr, *hTLKh = nullptr, *hPress = nullptr, *ldist3 = nullptr, *hHs = nullptr, *hPsiAvg = nullptr;
+           *hTm = nullptr, *hTLK = nullptr, *hTLKh = nullptr, *hPress = nullptr, *ldist3 = nullptr, *hHs = nullptr, *hPsiAvg = nullptr, *hInv = nullptr;
     // device-only
     double *bestH = nullptr, *SeOld = nullptr, *wFlow = nullptr, *lgeom = nullptr, *mval = nullptr,
            *b = nullptr, *cap = nullptr, *x0 = nullptr, *x1 = nullptr, *partA = nullptr, *partB = nullptr,
@@ -140,7 +140,7 @@ void fill_view()
         v.lwFlux = S.lwFlux; v.lvFlux = S.lvFlux; v.lfluxes = S.lfluxes.d; v.hdiag = S.hdiag;
         v.hTVK = S.hTVK; v.hIVK = S.hIVK; v.hCond = S.hCond;
         v.hTm = S.hTm; v.hTLK = S.hTLK; v.hTLKh = S.hTLKh; v.hPress = S.hPress; v.ldist3 = S.ldist3;
-        v.hHs = S.hHs; v.hPsiAvg = S.hPsiAvg;
+        v.hHs = S.hHs; v.hPsiAvg = S.hPsiAvg; v.hInv = S.hInv;
     }
 }
 
@@ -275,7 +275,7 @@ void release_all()
     S.T.release(); S.oldT.release(); S.hSink.release(); S.lfluxes.release();
     collect_heat_mirrors();
     for (Mirror<double> *m : heat_boundary_mirrors) m->release();
-    { double **hd[] = {&S.hFlux, &S.lwFlux, &S.lvFlux, &S.hdiag, &S.hTVK, &S.hIVK, &S.hCond, &S.hTm, &S.hTLK, &S.hTLKh, &S.hPress, &S.ldist3, &S.hHs, &S.hPsiAvg}; for (double **p : hd) { dev_free(*p); *p = nullptr; } }
+    { double **hd[] = {&S.hFlux, &S.lwFlux, &S.lvFlux, &S.hdiag, &S.hTVK, &S.hIVK, &S.hCond, &S.hTm, &S.hTLK, &S.hTLKh, &S.hPress, &S.ldist3, &S.hHs, &S.hPsiAvg, &S.hInv}; for (double **p : hd) { dev_free(*p); *p = nullptr; } }
     S.hfTypesAllocated = 0;
     double **devOnly[] = {&S.bestH, &S.SeOld, &S.wFlow, &S.lgeom, &S.mval, &S.b, &S.cap, &S.x0, &S.x1,
                           &S.partA, &S.partB, &S.scratch};
@@ -345,7 +345,7 @@ uint8_t sf3d_initialize(uint32_t nrNodes, uint32_t nrSurfaceNodes, uint8_t nrLat
             // link operands of the logarithmic means: value + logarithm per node (SF3DPair, sf3d_view.h)
             S.hTVK = (double *)dev_alloc(N * 16); S.hIVK = (double *)dev_alloc(N * 16); S.hCond = (double *)dev_alloc(N * 16);
             S.hTm = (double *)dev_alloc(N * 8); S.hTLK = (double *)dev_alloc(N * 16); S.hTLKh = (double *)dev_alloc(N * 16);
-            S.hHs = (double *)dev_alloc(N * 8); S.hPsiAvg = (double *)dev_alloc(N * 8);
+            S.hHs = (double *)dev_alloc(N * 8); S.hPsiAvg = (double *)dev_alloc(N * 8); S.hInv = (double *)dev_alloc(N * 8);
             S.hPress = (double *)dev_alloc(N * 8); S.ldist3 = (double *)dev_alloc(L * 8);
             S.lwFlux = (double *)dev_alloc(L * 8); S.lvFlux = (double *)dev_alloc(L * 8);
             S.hfTypesAllocated = (S.hfMode == 2) ? 9 : 1;
@@ -813,7 +813,7 @@ static SF3DView host_view()
     v.soil = S.soils.data();
     v.wrcModel = g_params.wrcModel;
     v.computeHeatVapor = S.heatVapor;
-    v.hPress = nullptr; v.ldist3 = nullptr; v.hTm = v.hTLK = v.hTLKh = nullptr; v.hHs = v.hPsiAvg = nullptr;      // device-only tables
+    v.hPress = nullptr; v.ldist3 = nullptr; v.hTm = v.hTLK = v.hTLKh = nullptr; v.hHs = v.hPsiAvg = v.hInv = nullptr;      // device-only tables
     return v;
 }
 uint8_t sf3d_set_node_heat_sink_source(uint32_t i, double q)

@@ -476,7 +476,10 @@ __global__ void kern_rule_boundary(Ctrl *c) { c->boundarySum = c->red[0]; }
 // registers and 1536 / 2048 resident threads per SM (a few spilled words) than unconstrained at 64 / 54
 // registers (profiles/r01_occupancy_ab.json).
 #ifndef SF3D_HEAT_ASSEMBLE_BLOCKS
-#define SF3D_HEAT_ASSEMBLE_BLOCKS 4
+#define SF3D_HEAT_ASSEMBLE_BLOCKS 6
+#endif
+#ifndef SF3D_HEAT_BLOCKS
+#define SF3D_HEAT_BLOCKS 8          // same finding for the heat rows (profiles/r01_occupancy_ab.json)
 #endif
 #ifndef SF3D_ASSEMBLE_BLOCKS
 #define SF3D_ASSEMBLE_BLOCKS 6
@@ -507,6 +510,17 @@ __global__ void __launch_bounds__(SF3D_BLOCK, HEAT ? SF3D_HEAT_ASSEMBLE_BLOCKS :
             v.ctrl->ticket = 0;
         }
     }
+}
+
+// coupled heat: thermal liquid / vapour fluxes of every soil row (invariantFluxes of the water system), before the
+// assembly of each approximation
+#ifndef SF3D_THERMAL_BLOCKS
+#define SF3D_THERMAL_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(SF3D_BLOCK, SF3D_THERMAL_BLOCKS) kern_thermal_invariant(SF3DView v)
+{
+    for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
+        if (!(v.world > 1 && META_GHOST(v.meta[i]))) sf3d_row_thermal_invariant(v, i);
 }
 
 // one Jacobi sweep (Water::JacobiWaterCPU) + the stopping rule of CPUSolver::solveLinearSystem
@@ -856,9 +870,6 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_build_grid(SF3DView v, GridDe
 // ------------------------------------------------------------------------------------------
 // coupled heat (Heat::*, CPUSolver::heatLoop)
 // ------------------------------------------------------------------------------------------
-#ifndef SF3D_HEAT_BLOCKS
-#define SF3D_HEAT_BLOCKS 8          // same finding for the heat rows (profiles/r01_occupancy_ab.json)
-#endif
 __global__ void __launch_bounds__(SF3D_BLOCK) kern_update_conductance(SF3DView v)
 {
     for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
@@ -1384,6 +1395,7 @@ void k_assemble(const SF3DView &v, double dt, int approx, double dtMin)
     const CommDev cm = comm_dev();
     {
         ProfScope ps(SF3D_K_ASSEMBLE);
+        if (v.computeHeat) { kern_thermal_invariant<<<GRID(v.N)>>>(v); LAUNCH_CHECK(); }
         if (v.computeHeat) kern_assemble<true><<<WIDE_GRID(v.N)>>>(v, dt, approx, dtMin, cm);
         else kern_assemble<false><<<WIDE_GRID(v.N)>>>(v, dt, approx, dtMin, cm);
         LAUNCH_CHECK();

@@ -447,9 +447,6 @@ SF3D_HD uint32_t sf3d_col_index(const SF3DView &v, const int32_t *__restrict__ o
     return off ? (uint32_t)((int64_t)i + off[c]) : v.mcol[(size_t)c * v.N + i];
 }
 
-#ifndef SF3D_HEAT_ASSEMBLE_GROUP
-#define SF3D_HEAT_ASSEMBLE_GROUP 2      // must divide 10
-#endif
 // soil row: every link is a redistribution except an Up link to a surface node (infiltration).
 // The ten neighbour conductivities are gathered first (independent loads), then the means.
 template <bool HEAT>
@@ -460,47 +457,31 @@ SF3D_HD double sf3d_row_assemble_soil(const SF3DView &v, uint32_t i, double dt, 
     const size_t N = v.N;
     const double ki = v.K[i];
     const int32_t *off = sf3d_row_pattern(v, i);
-    double sum = 0., invariant = 0.;
-    SF3DPair tli = {0., 0.}, tvi = {0., 0.};
-    double tmi = 0.;
-    if (HEAT) { tli = h_pair_load(v.hTLK, i); tmi = v.hTm[i]; if (v.computeHeatVapor) tvi = h_pair_load(v.hTVK, i); }
-    // links are handled in groups: all gathers of a group are issued before its arithmetic (independent loads in
-    // flight).  Water only: two groups of five; with the heat coupling every link carries five more operands
-    // (thermal liquid / vapour conductivity pairs, mean temperature), so the groups are shorter to stay in registers
-    constexpr int G = HEAT ? SF3D_HEAT_ASSEMBLE_GROUP : 5;
+    double sum = 0.;
+    // links are handled in two groups of five: all gathers of a group are issued before its arithmetic
+    // (independent loads in flight)
     #pragma unroll
-    for (int base = 0; base < SF3D_NLINK; base += G)
+    for (int half = 0; half < 2; ++half)
     {
-        uint32_t j[G];
-        double g[G], kj[G];
-        SF3DPair tl[G], tv[G];
-        double tm[G];
+        uint32_t j[5];
+        double g[5], kj[5];
         #pragma unroll
-        for (int q = 0; q < G; ++q)
+        for (int q = 0; q < 5; ++q)
         {
-            const int c = base + q;
+            const int c = half * 5 + q;
             j[q] = sf3d_col_index(v, off, i, c);
             g[q] = SF3D_LDS(v.lgeom + (size_t)c * N + i);
         }
         #pragma unroll
-        for (int q = 0; q < G; ++q) kj[q] = v.K[j[q]];
-        if (HEAT)
-        {
-            #pragma unroll
-            for (int q = 0; q < G; ++q)
-            {
-                tl[q] = h_pair_load(v.hTLK, j[q]); tm[q] = v.hTm[j[q]];
-                if (v.computeHeatVapor) tv[q] = h_pair_load(v.hTVK, j[q]); else { tv[q].v = 0.; tv[q].l = 0.; }
-            }
-        }
+        for (int q = 0; q < 5; ++q) kj[q] = v.K[j[q]];
         #pragma unroll
-        for (int q = 0; q < G; ++q)
+        for (int q = 0; q < 5; ++q)
         {
-            const int c = base + q;
+            const int c = half * 5 + q;
             const int slot = sf3d_slot_of_col(c);
             double kc;
-            if (c == 0 && j[q] < v.Ns)                    // first soil layer: link to the surface node above
-                kc = sf3d_infiltration(v, j[q], i, dt, v.larea[i], g[q]);
+            if (c == 0 && j[0] < v.Ns)                    // first soil layer: link to the surface node above
+                kc = sf3d_infiltration(v, j[0], i, dt, v.larea[i], g[0]);
             else
             {
 #ifdef SF3D_REFERENCE_ROUNDING
@@ -509,12 +490,14 @@ SF3D_HD double sf3d_row_assemble_soil(const SF3DView &v, uint32_t i, double dt, 
                 const double area = 0.;
 #endif
                 kc = sf3d_redistribution(v, ki, kj[q], slot, area, g[q]);
-                if (HEAT && j[q] != i) invariant += sf3d_heat_thermal_invariant(v, i, slot, tli, tvi, tmi, tl[q], tv[q], tm[q]);
             }
             k[c * kstride] = kc;
             sum += kc;                                    // zero entries are not stored in the reference; +0 is exact
         }
     }
+    // with the heat coupling: the row's thermal liquid / vapour fluxes (water.cpp:329-340), summed in the same link
+    // order by sf3d_row_thermal_invariant (its own pass: it needs few registers, this one many)
+    const double invariant = HEAT ? v.hInv[i] : 0.;
     sf3d_row_store(v, i, dt, k, kstride, sum, invariant);
     return 0.;
 }

@@ -31,6 +31,10 @@
 #define SF3D_HEAT_LINK_UNROLL 1      // link loops of the heat rows
 #endif
 constexpr int kHeatLinkUnroll = SF3D_HEAT_LINK_UNROLL;
+#ifndef SF3D_THERMAL_UNROLL
+#define SF3D_THERMAL_UNROLL 2        // link loop of the thermal invariant fluxes
+#endif
+constexpr int kThermalUnroll = SF3D_THERMAL_UNROLL;
 
 // pow() with the small integer exponents heat.cpp passes: the product multiplies, the reference-rounding
 // build calls the library like the reference does
@@ -363,6 +367,30 @@ SF3D_HD double sf3d_heat_thermal_invariant(const SF3DView &v, uint32_t i, int sl
     double f = h_link_flux(v, i, slot, h_pair_mean(tli, tlj) * dT);
     if (v.computeHeatVapor) f += h_link_flux(v, i, slot, h_pair_mean(tvi, tvj) * dT) / HC_WATER_DENSITY;
     return f;
+}
+
+// one soil row's invariant fluxes of the water system: thermal liquid (+ thermal vapour / rho_w) flux of every
+// soil-soil link, accumulated in the reference's link order (Up, Lateral 0..7, Down: computeLinearSystemElement,
+// cpusolver.cpp:352-374, through computeLinkFluxes, water.cpp:329-340).  Operands were stored by the node phase.
+SF3D_HD void sf3d_row_thermal_invariant(const SF3DView &v, uint32_t i)
+{
+    if (i < v.Ns) return;
+    const int32_t *off = sf3d_row_pattern(v, i);
+    const SF3DPair tli = h_pair_load(v.hTLK, i);
+    SF3DPair tvi = {0., 0.};
+    if (v.computeHeatVapor) tvi = h_pair_load(v.hTVK, i);
+    const double tmi = v.hTm[i];
+    double invariant = 0.;
+    #pragma unroll kThermalUnroll
+    for (int c = 0; c < SF3D_NLINK; ++c)
+    {
+        const uint32_t j = sf3d_col_index(v, off, i, c);
+        if (j == i || j < v.Ns) continue;                   // absent link, or the infiltration link of the first soil layer
+        SF3DPair tvj = {0., 0.};
+        if (v.computeHeatVapor) tvj = h_pair_load(v.hTVK, j);
+        invariant += sf3d_heat_thermal_invariant(v, i, sf3d_slot_of_col(c), tli, tvi, tmi, h_pair_load(v.hTLK, j), tvj, v.hTm[j]);
+    }
+    v.hInv[i] = invariant;
 }
 
 // computeNodeAtmosphericLatentVaporFlux (heat.cpp:988-1007), node = HeatSurface soil node

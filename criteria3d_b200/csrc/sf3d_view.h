@@ -160,6 +160,7 @@ struct SF3DView {
     // water-side coupling, stored by the node phase: mean temperature and thermal liquid conductivity
     // (mean T, current psi); heat side: thermal liquid conductivity (T, sub-step averaged psi)
     double *hTm, *hTLK, *hTLKh;
+    double *hInv;                   // water side: the row's thermal liquid / vapour flux sum (invariantFluxes, water.cpp:329-340)
     double *hHs, *hPsiAvg;          // heat side, per sub-step: getNodeH_fromTimeSteps and the sub-step averaged matric head
     double *hPress;                 // static: pressureFromAltitude(z), heat.cpp:1117
     double *ldist3;                 // static per link, slot-major: nodeDistance3D (soilPhysics.cpp:331-335); device math

@@ -30,7 +30,7 @@ def setup_slab(sf: SoilFluxes3D, rows: int, cols: int, n_soil_layers: int, rank:
     The balance is initialised after the ghosts are known so that storage counts owned nodes only."""
     slab = make_slab(rows, cols, n_soil_layers, world, rank)
     cat = slab_catchment(slab, **cat_kw)
-    setup(sf, cat, numerics=numerics)
+    setup(sf, cat, numerics=numerics, balance=(world == 1))
     if world > 1:
         peers, send, recv = slab.halo()
         _ok(sf.set_halo(peers, send, recv, slab.n_global), "sf3d_ext_set_halo")

@@ -236,7 +236,7 @@ class Catchment:
 
 
 def setup(sf: SoilFluxes3D, cat: Catchment, threads: int = 0,
-          numerics: tuple | None = None, heat_flux_mode: int | None = None) -> None:
+          numerics: tuple | None = None, heat_flux_mode: int | None = None, balance: bool = True) -> None:
     """initialize3DModel's call sequence (project3D.cpp:456-616) on implementation `sf`."""
     hf = HeatFluxSaveMode.Total if cat.heat else HeatFluxSaveMode.None_
     if heat_flux_mode is not None:
@@ -259,7 +259,8 @@ def setup(sf: SoilFluxes3D, cat: Catchment, threads: int = 0,
     _ok(sf.set_field(Field.MATRIC_POTENTIAL, 0, cat.initial_matric_potential()), "initial matric potential")
     if cat.heat:
         setup_heat(sf, cat, mode=int(hf))
-    _ok(sf.initializeBalance(), "initializeBalance")
+    if balance:         # row slabs initialise the balance after the halo is wired (reductions over ranks)
+        _ok(sf.initializeBalance(), "initializeBalance")
 
 
 def setup_heat(sf: SoilFluxes3D, cat: Catchment, hour: int = 0, advection: bool = False, latent: bool = True,
