@@ -38,6 +38,7 @@ static cudaStream_t g_stream = nullptr;
 static int g_device = -1;
 static uint64_t g_launches = 0;
 static Ctrl *g_ctrlPinned = nullptr;
+static unsigned long long g_commNsSeen = 0, g_commCountSeen = 0;
 
 #define CUDA_OK(call)                                                                          \
     do {                                                                                       \
@@ -426,10 +427,17 @@ __global__ void kern_p2p_allreduce(CommDev cm, int count, int isMax, double *val
 }
 // called by EVERY thread of the block that finished last, after thread 0 wrote the local values into c->red[]:
 // folds the all-reduce over ranks into the producing kernel (no extra launch per reduction)
+__device__ __forceinline__ unsigned long long global_ns()
+{ unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ void last_block_allreduce(const CommDev &cm, Ctrl *c, int count, int isMax)
 {
     __syncthreads();
-    if (threadIdx.x < 32) p2p_allreduce_warp(cm, count, isMax, c->red, c);
+    if (threadIdx.x < 32)
+    {
+        const unsigned long long t0 = global_ns();
+        p2p_allreduce_warp(cm, count, isMax, c->red, c);
+        if (threadIdx.x == 0) { c->commNs += global_ns() - t0; c->commCount += 1ull; }
+    }
     __syncthreads();
 }
 
@@ -593,7 +601,9 @@ __global__ void __launch_bounds__(SF3D_BLOCK, SF3D_JACOBI_BLOCKS) kern_jacobi_mu
     if (v.ctrl->status != SOLVE_RUNNING) return;        // same decision on every rank: the status derives from all-reduced values
     __shared__ double sh[SF3D_BLOCK / 32];
     double norm = 0.;
-    for (uint32_t k = blockIdx.x * SF3D_BLOCK + threadIdx.x; k < e.nBoundary; k += gridDim.x * SF3D_BLOCK)
+    // (the LAST blocks of the grid take the boundary rows: the interior loop below gives the first blocks one more
+    // trip when the rows do not divide evenly, so the extra work goes where there is slack)
+    for (uint32_t k = (gridDim.x - 1u - blockIdx.x) * SF3D_BLOCK + threadIdx.x; k < e.nBoundary; k += gridDim.x * SF3D_BLOCK)
     {
         const uint32_t i = e.bIdx[k];
         double xn;
@@ -604,6 +614,10 @@ __global__ void __launch_bounds__(SF3D_BLOCK, SF3D_JACOBI_BLOCKS) kern_jacobi_mu
             const uint32_t r = e.remote[p][k];
             if (r != SF3D_NO_REMOTE) e.peerX[p][r] = xn;
         }
+        // system-scope fence by the threads that stored into peer memory, right here (early in the kernel, behind
+        // other warps' work): these stores are then ordered before this block's ticket below and, through the last
+        // block's own fence, before the sequence number the peers wait for
+        __threadfence_system();
     }
     for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
     {
@@ -613,7 +627,6 @@ __global__ void __launch_bounds__(SF3D_BLOCK, SF3D_JACOBI_BLOCKS) kern_jacobi_mu
     }
     norm = block_reduce<HEAT>(norm, sh);
     if (threadIdx.x == 0) v.partA[blockIdx.x] = norm;
-    __threadfence_system();                             // this block's peer stores before its ticket
     if (last_block(v.ctrl))
     {
         const double total = fold_partials<HEAT>(v.partA, sh);
@@ -1535,6 +1548,13 @@ void read_ctrl(const SF3DView &v, Ctrl *out)
     CUDA_OK(cudaStreamSynchronize(g_stream));
     if (g_prof && g_pending.size() > 4096) prof_resolve();
     *out = *g_ctrlPinned;
+    if (g_prof && out->commCount >= g_commCountSeen)
+    {
+        // device-side clocks of the in-kernel all-reduces since the last read (see Ctrl::commNs)
+        g_profMs[SF3D_K_COMM] += (double)(out->commNs - g_commNsSeen) * 1e-6;
+        g_profN[SF3D_K_COMM] += out->commCount - g_commCountSeen;
+    }
+    g_commNsSeen = out->commNs; g_commCountSeen = out->commCount;
     if (out->commError)
         throw DeviceError{-3, "a row-slab peer did not answer within the mailbox time-out (SF3D_MAILBOX_TIMEOUT_S): "
                               "the step was abandoned, the state is undefined", "all-reduce over ranks"};

@@ -108,6 +108,10 @@ struct Ctrl {
     unsigned int ticket;    // last-block election counter
     int    commError;       // multi-GPU: set when a mailbox all-reduce timed out; read_ctrl turns it into a DeviceError
     double red[4];          // multi-GPU: local reductions handed to the all-reduce before the rule is applied
+    // multi-GPU: device-side clocks of the in-kernel all-reduces (globaltimer, ns): time between the election of the
+    // last block (all rows of this rank done) and the end of the all-reduce = wait for the slowest rank + NVLink
+    // latency; summed over the all-reduces executed, with their count.  Reported as kernel kind "comm".
+    unsigned long long commNs, commCount;
 };
 
 struct SF3DView {
