@@ -182,6 +182,10 @@ void upload_tables()
 // everything the kernels read must be current on the device
 uint8_t sync_to_device(bool finalizeTopology = true)
 {
+    // anything set on the host since the last step that the next try's first pass depends on: that pass must run
+    if (S.tablesDirty || S.topoDirty || S.H.hostNewer || S.oldH.hostNewer || S.Se.hostNewer || S.z.hostNewer || S.size.hostNewer
+        || S.tab.hostNewer || S.meta.hostNewer)
+        S.eng.tryPrepared = false;
     upload_tables();
     S.x.push(); S.y.push(); S.z.push(); S.size.push(); S.meta.push(); S.tab.push();
     S.bSlope.push(); S.bSize.push(); S.bRate.push(); S.bSum.push(); S.bPresc.push();
@@ -361,6 +365,7 @@ uint8_t sf3d_initialize(uint32_t nrNodes, uint32_t nrSurfaceNodes, uint8_t nrLat
         S.eng.p = &g_params;
         S.eng.computeWater = S.water;
         S.eng.computeHeat = S.heat;
+        S.eng.tryPrepared = false;
         fill_view();
         return SF3D_OK;
     }, (uint8_t)SF3D_MEMORY_ERROR);
@@ -979,6 +984,7 @@ uint8_t sf3d_ext_set_field(int field, uint32_t first, uint32_t count, const doub
                 double *tmp = scratch_buffer();
                 h2d(tmp, src, (size_t)count * sizeof(double));
                 k_set_potential(S.eng.v, first, count, tmp, field == SF3D_F_TOTAL_POTENTIAL);
+                S.eng.tryPrepared = false;
                 S.H.dev_written(); S.oldH.dev_written(); S.Se.dev_written(); S.K.dev_written();
                 return SF3D_OK;
             }

@@ -3,6 +3,7 @@
 // reduced scalars (Courant max, residual status, storage, sink sum) are read back: two to three
 // stream synchronisations per Picard approximation.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include "sf3d_engine.h"
@@ -199,7 +200,8 @@ bool Engine::waterMainLoop(double maxTimeStep, double &acceptedTimeStep)
     while (stepStatus != BalanceResult::Accepted)
     {
         acceptedTimeStep = std::min(p->deltaTcurr, maxTimeStep);
-        k_begin_try(v);                 // oldH = H ; x = H ; Se ; surface capacity
+        if (!tryPrepared) k_begin_try(v);                 // oldH = H ; x = H ; Se ; surface capacity
+        tryPrepared = false;
         xcur = 0;
         ++cnt.tries;
         if (computeHeat) k_update_conductance(v);       // cpusolver.cpp:171-173
@@ -366,7 +368,9 @@ void Engine::acceptStep(double deltaT)
     prevStep.waterStorage = curStep.waterStorage;
     prevStep.waterSinkSource = curStep.waterSinkSource;
     curPeriod.waterSinkSource += curStep.waterSinkSource;
-    k_accept(v, deltaT);
+    static const bool fuse = getenv("SF3D_NO_PREPARED_TRY") == nullptr;
+    tryPrepared = fuse && !computeHeat;
+    k_accept(v, deltaT, tryPrepared);
 }
 
 // Water::restoreBestStep (water.cpp:253-267)

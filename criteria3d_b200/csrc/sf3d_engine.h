@@ -26,6 +26,9 @@ struct Engine {
     sf3d_counters cnt{};
     int xcur = 0;                           // which of x0/x1 holds the current solution vector
     int lastSweeps = 6;                     // sweeps of the previous solve (launch batching hint)
+    // the accept pass of the previous step already did the next try's first pass (oldH = H, x = H, SeOld = Se); cleared
+    // by anything that touches the state in between (setters, restore, re-initialisation)
+    bool tryPrepared = false;
     bool computeWater = true;
     bool computeHeat = false;
     // per-node heat coefficients (kern_heat_coeffs) currently stored for this heat sub-step length, with the current

@@ -358,27 +358,32 @@ __global__ void __launch_bounds__(SF3D_BLOCK, SF3D_NODE_BLOCKS) kern_node_phase(
 // ---- row-slab ranks: device side of the peer-memory all-reduce ---------------------------------------
 // Every rank owns a mailbox that all ranks can write through CUDA IPC (NVLink peer stores).
 #define SF3D_MAX_RANKS 16
+// One 8-byte mailbox word carries 32 bits of payload and a 32-bit tag derived from the sequence number: an aligned
+// 8-byte store is single-copy atomic, also over NVLink, so a reader that sees the expected tag has the payload of
+// the same store and no fence is needed between "data" and "flag" (the scheme of NCCL's LL protocol).
 struct Mbox {
-    double val[2][SF3D_MAX_RANKS][4];
-    unsigned long long seq[2][SF3D_MAX_RANKS];
+    unsigned long long word[2][SF3D_MAX_RANKS][8];      // [parity][source rank][value k: low half 2k, high half 2k + 1]
     unsigned long long localSeq;        // all-reduces executed by THIS rank so far (only this rank touches it)
     int error; int pad;
 };
 // kernel parameter of the reducing kernels.  mine == nullptr: the reduction over ranks is finished by separate
 // launches (NCCL, or the separate-kernel peer-memory path kept for A/B), the kernel only leaves its local value
 // in Ctrl::red
-struct CommDev { Mbox *mine; Mbox *const *peers; int rank, world; long long timeoutCycles; };
+struct CommDev { Mbox *mine; Mbox *const *peers; int rank, world; long long timeoutCycles; int dbg; };
 
-// All-reduce of up to four doubles over peer memory, executed by ONE warp: lane r stores this rank's values and
-// then the sequence number into rank r's mailbox (system-scope fence in between) and waits until rank r's
-// contribution for the same sequence number has landed in the local mailbox; lane 0 folds the contributions in
-// rank order, so every rank obtains the bit-identical result and takes the same decisions.  The sequence number
-// counts the all-reduces this rank has EXECUTED (device side: launches that return early on every rank, e.g.
-// sweeps enqueued after convergence, do not consume one), so consecutive all-reduces always use different slots
-// and a rank can be at most one all-reduce ahead of its slowest peer.  The wait is bounded
-// (SF3D_MAILBOX_TIMEOUT_S, default 20 s of SM clocks): on expiry Ctrl::commError is set and the status becomes
-// SOLVE_COMM_ERROR, which the host turns into an error return (read_ctrl throws) -- never into a numerical
-// "halve the time step" event.
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+
+// All-reduce of up to four doubles over peer memory, executed by ONE warp.  Every (destination rank, value, half)
+// triple is one tagged 8-byte word; the lanes store this rank's words into all mailboxes over NVLink (one release
+// fence at system scope first: it orders the halo rows every block of this kernel stored into peer memory -- the
+// blocks' tickets were observed by this block -- before the words the peers wait for), then wait until every
+// rank's words for the same sequence number have landed in the local mailbox; lanes k < count fold value k in rank
+// order, so every rank obtains the bit-identical result and takes the same decisions.  The sequence number counts
+// the all-reduces this rank has EXECUTED (device side: launches that return early on every rank, e.g. sweeps
+// enqueued after convergence, do not consume one), so consecutive all-reduces use different parities and a rank can
+// be at most one all-reduce ahead of its slowest peer.  The wait is bounded (SF3D_MAILBOX_TIMEOUT_S, default 20 s
+// of SM clocks): on expiry Ctrl::commError is set and the status becomes SOLVE_COMM_ERROR, which the host turns
+// into an error return (read_ctrl throws) -- never into a numerical "halve the time step" event.
 __device__ __forceinline__ void p2p_allreduce_warp(const CommDev &cm, int count, int isMax, double *values, Ctrl *ctrl)
 {
     const int lane = threadIdx.x & 31;
@@ -388,36 +393,47 @@ __device__ __forceinline__ void p2p_allreduce_warp(const CommDev &cm, int count,
     seq = __shfl_sync(0xffffffffu, seq, 0);
     timedOut = __shfl_sync(0xffffffffu, timedOut, 0);       // sticky: after one time-out no further waiting
     const int par = (int)(seq & 1ull);
-    if (!timedOut && lane < cm.world)
+    const unsigned long long tag = ((seq % 0xFFFFFFFFull) + 1ull) << 32;    // never 0 (a fresh mailbox is all zero)
+    const int perRank = 2 * count, nWords = cm.world * perRank;
+    if (!timedOut)
     {
-        Mbox *dst = cm.peers[lane];
-        for (int k = 0; k < count; ++k) *((volatile double *)&dst->val[par][cm.rank][k]) = values[k];
-        __threadfence_system();
-        *((volatile unsigned long long *)&dst->seq[par][cm.rank]) = seq;
+        fence_acq_rel_sys();
+        for (int w = lane; w < nWords; w += 32)
+        {
+            const int r = w / perRank, q = w - r * perRank;
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(values[q >> 1]);
+            const unsigned long long half = (q & 1) ? (bits >> 32) : (bits & 0xFFFFFFFFull);
+            *((volatile unsigned long long *)&cm.peers[r]->word[par][cm.rank][q]) = tag | half;
+        }
         const long long t0 = clock64();
-        while (*((volatile unsigned long long *)&cm.mine->seq[par][lane]) != seq)
-            if (clock64() - t0 > cm.timeoutCycles) { timedOut = 1; break; }
+        for (int w = lane; w < nWords; w += 32)
+        {
+            const int r = w / perRank, q = w - r * perRank;
+            while ((*((volatile unsigned long long *)&cm.mine->word[par][r][q]) & 0xFFFFFFFF00000000ull) != tag)
+                if (clock64() - t0 > cm.timeoutCycles) { timedOut = 1; break; }
+        }
     }
     timedOut = __any_sync(0xffffffffu, timedOut);
-    __threadfence_system();
-    if (lane == 0)
+    fence_acq_rel_sys();
+    if (timedOut)
     {
-        if (timedOut)
+        if (lane == 0)
         {
             cm.mine->error = 1;
             if (ctrl) { ctrl->commError = 1; ctrl->status = SOLVE_COMM_ERROR; }
         }
-        else
-            for (int k = 0; k < count; ++k)
-            {
-                double acc = *((volatile double *)&cm.mine->val[par][0][k]);
-                for (int r = 1; r < cm.world; ++r)
-                {
-                    const double x = *((volatile double *)&cm.mine->val[par][r][k]);
-                    acc = isMax ? ((acc < x) ? x : acc) : (acc + x);
-                }
-                values[k] = acc;
-            }
+    }
+    else if (lane < count)
+    {
+        double acc = 0.;
+        for (int r = 0; r < cm.world; ++r)
+        {
+            const unsigned long long lo = *((volatile unsigned long long *)&cm.mine->word[par][r][2 * lane]);
+            const unsigned long long hi = *((volatile unsigned long long *)&cm.mine->word[par][r][2 * lane + 1]);
+            const double x = __longlong_as_double((long long)((hi << 32) | (lo & 0xFFFFFFFFull)));
+            acc = (r == 0) ? x : (isMax ? ((acc < x) ? x : acc) : (acc + x));
+        }
+        values[lane] = acc;
     }
     __syncwarp();
 }
@@ -435,7 +451,7 @@ __device__ __forceinline__ void last_block_allreduce(const CommDev &cm, Ctrl *c,
     if (threadIdx.x < 32)
     {
         const unsigned long long t0 = global_ns();
-        p2p_allreduce_warp(cm, count, isMax, c->red, c);
+        if (!(cm.dbg & 8)) p2p_allreduce_warp(cm, count, isMax, c->red, c);
         if (threadIdx.x == 0) { c->commNs += global_ns() - t0; c->commCount += 1ull; }
     }
     __syncthreads();
@@ -584,6 +600,7 @@ struct ExchangeDev {
     int nPeers;
     const uint32_t *remote[SF3D_MAX_HALO_PEERS];        // [nBoundary] id of the row in peer p's numbering, or SF3D_NO_REMOTE
     double *peerX[SF3D_MAX_HALO_PEERS];                 // peer p's OUTPUT solution buffer of this sweep
+    int dbg;                                            // SF3D_MULTI_DEBUG (timing experiments only; results invalid when set)
 };
 __device__ __forceinline__ void rule_heat_jacobi(Ctrl *c, double norm, int maxIter, double tol)
 {
@@ -601,27 +618,31 @@ __global__ void __launch_bounds__(SF3D_BLOCK, SF3D_JACOBI_BLOCKS) kern_jacobi_mu
     if (v.ctrl->status != SOLVE_RUNNING) return;        // same decision on every rank: the status derives from all-reduced values
     __shared__ double sh[SF3D_BLOCK / 32];
     double norm = 0.;
-    // (the LAST blocks of the grid take the boundary rows: the interior loop below gives the first blocks one more
-    // trip when the rows do not divide evenly, so the extra work goes where there is slack)
-    for (uint32_t k = (gridDim.x - 1u - blockIdx.x) * SF3D_BLOCK + threadIdx.x; k < e.nBoundary; k += gridDim.x * SF3D_BLOCK)
+    // (boundary row k goes to thread k / gridDim.x of block k % gridDim.x: every block takes the same share in its
+    // lowest warps, so no block starts its interior rows a whole dependent-load chain later than the others;
+    // measured against "one row per thread of the last blocks": 6.5 us per sweep)
+    for (uint32_t k = ((e.dbg & 16) ? (gridDim.x - 1u - blockIdx.x) * SF3D_BLOCK + threadIdx.x : threadIdx.x * gridDim.x + blockIdx.x);
+         k < ((e.dbg & 4) ? 0u : e.nBoundary); k += gridDim.x * SF3D_BLOCK)
     {
         const uint32_t i = e.bIdx[k];
         double xn;
         const double d = HEAT ? sf3d_row_heat_jacobi(v, i, xin, xout, &xn) : sf3d_row_jacobi(v, i, xin, xout, &xn);
         norm = HEAT ? ((norm < d) ? d : norm) : (norm + d);
-        for (int p = 0; p < e.nPeers; ++p)
+        #pragma unroll
+        for (int p = 0; p < SF3D_MAX_HALO_PEERS; ++p)
         {
+            if (p >= e.nPeers) break;
             const uint32_t r = e.remote[p][k];
-            if (r != SF3D_NO_REMOTE) e.peerX[p][r] = xn;
+            if (r != SF3D_NO_REMOTE && !(e.dbg & 1)) e.peerX[p][r] = xn;
         }
         // system-scope fence by the threads that stored into peer memory, right here (early in the kernel, behind
         // other warps' work): these stores are then ordered before this block's ticket below and, through the last
         // block's own fence, before the sequence number the peers wait for
-        __threadfence_system();
+        if (!(e.dbg & 2)) __threadfence_system();
     }
     for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
     {
-        if (v.pid[i] & SF3D_PID_SKIP) continue;         // ghost row, or boundary row already done above
+        if ((e.dbg & 4) ? (v.pid[i] == SF3D_GHOST_PID) : ((v.pid[i] & SF3D_PID_SKIP) != 0)) continue;         // ghost row, or boundary row already done above
         const double d = HEAT ? sf3d_row_heat_jacobi(v, i, xin, xout) : sf3d_row_jacobi(v, i, xin, xout);
         norm = HEAT ? ((norm < d) ? d : norm) : (norm + d);
     }
@@ -692,10 +713,16 @@ __global__ void __launch_bounds__(SF3D_BLOCK, SF3D_POST_BLOCKS) kern_post(SF3DVi
     }
 }
 
+// PREP: the copies of the next try's first pass (kern_begin_try) ride on this pass (water-only runs: the heat step
+// still reads the previous heads after the water step is accepted)
+template <bool PREP>
 __global__ void __launch_bounds__(SF3D_BLOCK) kern_accept(SF3DView v, double dt)
 {
     for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
+    {
         if (!(v.world > 1 && META_GHOST(v.meta[i]))) sf3d_row_accept(v, i, dt);
+        if (PREP) sf3d_row_prepare_try(v, i);
+    }
 }
 
 __global__ void __launch_bounds__(SF3D_BLOCK) kern_restore_best(SF3DView v)
@@ -1246,6 +1273,8 @@ static CommDev comm_dev_full()
 {
     CommDev c{};
     c.mine = g_mbox; c.peers = g_peerMboxDev; c.rank = g_rank; c.world = g_world; c.timeoutCycles = g_timeoutCycles;
+    static const int dbg = getenv("SF3D_MULTI_DEBUG") ? atoi(getenv("SF3D_MULTI_DEBUG")) : 0;
+    c.dbg = dbg;
     return c;
 }
 // what the reducing kernels receive: the mailboxes when the all-reduce over ranks runs inside the producing kernel
@@ -1318,6 +1347,8 @@ static ExchangeDev exchange_dev(const double *xout)
 {
     const int b = (xout == g_localX[1]) ? 1 : 0;
     ExchangeDev e{};
+    static const int dbg = getenv("SF3D_MULTI_DEBUG") ? atoi(getenv("SF3D_MULTI_DEBUG")) : 0;
+    e.dbg = dbg;
     e.nBoundary = g_nBoundary; e.bIdx = g_bIdx; e.nPeers = (int)g_halo.size();
     for (size_t p = 0; p < g_halo.size(); ++p) { e.remote[p] = g_bRemote[p]; e.peerX[p] = g_halo[p].peerX[b]; }
     return e;
@@ -1447,7 +1478,12 @@ void k_post(const SF3DView &v, const double *x, double dt, int mode)
         kern_rule_post<<<1, 1, 0, g_stream>>>(v.ctrl); LAUNCH_CHECK();
     }
 }
-void k_accept(const SF3DView &v, double dt) { ProfScope ps(SF3D_K_ACCEPT); kern_accept<<<GRID(v.N)>>>(v, dt); LAUNCH_CHECK(); }
+void k_accept(const SF3DView &v, double dt, bool prepareNextTry)
+{
+    ProfScope ps(SF3D_K_ACCEPT);
+    if (prepareNextTry) kern_accept<true><<<GRID(v.N)>>>(v, dt); else kern_accept<false><<<GRID(v.N)>>>(v, dt);
+    LAUNCH_CHECK();
+}
 void k_restore_best(const SF3DView &v) { ProfScope ps(SF3D_K_OTHER); kern_restore_best<<<GRID(v.N)>>>(v); LAUNCH_CHECK(); }
 void k_total_boundary_flow(const SF3DView &v, uint32_t bt)
 {

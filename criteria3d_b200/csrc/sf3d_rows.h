@@ -601,6 +601,10 @@ SF3D_HD void sf3d_row_accept(const SF3DView &v, uint32_t i, double dt)
     const size_t N = v.N;
     const uint32_t m = v.meta[i];
     const double Hi = v.H[i];
+    // linked nodes from the row's link pattern (an existing link's matrix column is its link index; absent links have
+    // a zero entry and are skipped), so the explicit 4-byte link index array is not read
+    uint32_t j[SF3D_NLINK];
+    sf3d_row_cols(v, i, j);
     #pragma unroll
     for (int c = 0; c < SF3D_NLINK; ++c)
     {
@@ -608,10 +612,21 @@ SF3D_HD void sf3d_row_accept(const SF3DView &v, uint32_t i, double dt)
         if (!META_HAS_SLOT(m, slot)) continue;
         const double A = v.mval[(size_t)c * N + i];
         if (A == 0.) continue;
-        const uint32_t j = v.lidx[(size_t)slot * N + i];
-        v.lflow[(size_t)slot * N + i] += A * (Hi - v.H[j]) * dt;
+        v.lflow[(size_t)slot * N + i] += A * (Hi - v.H[j[c]]) * dt;
     }
     if (META_BT(m) != BT_NONE) v.bSum[i] += v.bRate[i] * dt;
+}
+
+// what the next try's first pass would do (sf3d_row_begin_try), done while the accepted state is at hand: after an
+// accepted step the stored Se IS computeNodeSe(H) (written by the post pass or by restore-best from the same H), so
+// the pass reduces to copies.  The engine skips kern_begin_try while nothing has touched the state in between.
+SF3D_HD void sf3d_row_prepare_try(const SF3DView &v, uint32_t i)
+{
+    const double H = v.H[i];
+    v.oldH[i] = H;
+    v.x0[i] = H;
+    if (i < v.Ns) v.cap[i] = v.size[i];
+    else v.SeOld[i] = v.Se[i];
 }
 
 // Water::restoreBestStep per node (water.cpp:255-263): H = best ; Se ; K

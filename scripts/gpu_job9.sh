@@ -1,0 +1,25 @@
+#!/bin/bash
+# round 2, GPU job 9 (2 GPUs): tagged-word mailbox all-reduce + boundary rows spread over all blocks: slab parity tests, then timing
+cd "$GRAFT_REPO_ROOT" || exit 1
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_slabs.py -q > gpurun_out/r2_slab_tests_9.txt 2>&1; tail -3 gpurun_out/r2_slab_tests_9.txt
+run() { # name, env...
+  local name=$1; shift
+  env "$@" timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29741 \
+      bench.py --gpus 2 --steps 20 --warmup 3 --no-c4 --no-cpu-baseline --no-parity-check > gpurun_out/r2_exp9_$name.json 2> gpurun_out/r2_exp9_$name.err
+  echo "$name rc=$?"
+}
+run base   SF3D_MULTI_DEBUG=0
+run oldboundary SF3D_MULTI_DEBUG=16
+run noreduce SF3D_MULTI_DEBUG=8
+run nothing SF3D_MULTI_DEBUG=15
+CUDA_VISIBLE_DEVICES=0 timeout 300 python bench.py --steps 20 --warmup 3 --no-c4 --no-cpu-baseline > gpurun_out/r2_exp9_n1.json 2> gpurun_out/r2_exp9_n1.err
+python - <<'PY'
+import json
+for f in ("n1","base","oldboundary","noreduce","nothing"):
+    try:
+        d=json.loads(open(f"gpurun_out/r2_exp9_{f}.json").read().strip().splitlines()[-1])
+        k=d["kernel_ms"]; n=d["sweeps"]
+        print(f"{f:10s} ms/step {d['ms_per_step']:.3f} sweeps {n} jacobi/sweep {1e3*k['jacobi']/n:.1f} us comm {k['comm']:.2f} asm {k['assemble']:.1f} post {k['post']:.1f} launches {d['gpu_launches']}")
+    except Exception as e: print(f, "failed", e)
+PY
