@@ -7,6 +7,17 @@
 #include <string.h>
 #include <algorithm>
 #include "sf3d_engine.h"
+#include <nvtx3/nvToolsExt.h>
+
+// NVTX ranges per phase of the step (tracing): visible in Nsight Systems / Compute timelines.  Header-only
+// NVTX3: without an attached tool the calls are no-ops; SF3D_NVTX=0 removes even those.
+namespace {
+const bool g_nvtx = !(getenv("SF3D_NVTX") && atoi(getenv("SF3D_NVTX")) == 0);
+struct Range {
+    explicit Range(const char *name) { if (g_nvtx) nvtxRangePushA(name); }
+    ~Range() { if (g_nvtx) nvtxRangePop(); }
+};
+}
 
 namespace sf3d {
 
@@ -40,6 +51,7 @@ uint32_t Engine::calcCurrentMaxIterationNumber(int approx) const
 // soilFluxes3D.cpp:1785-1821
 double Engine::computeStep(double maxTimeStep)
 {
+    Range r("sf3d computeStep");
     if (computeHeat)
     {
         k_reset_water_fluxes(v);            // resetFluxValues(false, true)
@@ -109,6 +121,7 @@ void Engine::runHeat(double maxTimeStep, double dtWater)
 // cap so that it reaches the tolerance whenever Gauss-Seidel does.
 bool Engine::heatLoop(double timeStepHeat, double timeStepWater)
 {
+    Range r("sf3d heat sub-step");
     k_heat_begin(v, timeStepHeat, timeStepWater, heatCoeffsCurrent && heatCoeffsDt == timeStepHeat);   // reset heat fluxes ; x = T ; oldT = T ; C
     heatCoeffsCurrent = false;                          // the solve below changes T
     k_heat_assemble(v, timeStepHeat, timeStepWater);
@@ -199,6 +212,7 @@ bool Engine::waterMainLoop(double maxTimeStep, double &acceptedTimeStep)
     BalanceResult stepStatus = BalanceResult::Refused;
     while (stepStatus != BalanceResult::Accepted)
     {
+        Range r("sf3d water try");
         acceptedTimeStep = std::min(p->deltaTcurr, maxTimeStep);
         if (!tryPrepared) k_begin_try(v);                 // oldH = H ; x = H ; Se ; surface capacity
         tryPrepared = false;
@@ -230,6 +244,7 @@ bool Engine::courantFailed(double /*deltaT*/, double courant)
 // sweeps are enqueued in batches and the control block is read back once per batch.
 int Engine::solveWater(int approx)
 {
+    Range r("sf3d water solve (Jacobi sweeps)");
     const int maxIter = (int)calcCurrentMaxIterationNumber(approx);
     const int start = xcur;
     int launched = 0;
@@ -263,6 +278,7 @@ BalanceResult Engine::waterApproximationLoop(double deltaT)
     for (int approxIdx = 0; approxIdx < (int)p->maxApproximationsNumber; ++approxIdx)
     {
         ++cnt.approximations;
+        Range r("sf3d water approximation");
         k_node_phase(v, deltaT, 1);                             // computeCapacity + updateBoundaryWaterData
         k_assemble(v, deltaT, approxIdx, p->deltaTmin);         // rows + Courant + normalisation
         const int status = solveWater(approxIdx);

@@ -166,3 +166,29 @@ def boundary_runoff(dem: np.ndarray, aspect: np.ndarray, nodata: float = -9999.0
 def boundary_slope_tan(slope_deg: np.ndarray) -> np.ndarray:
     """float boundarySlope = tan(slopeDegree * DEG_TO_RAD), Project3D::setCrit3DTopography (project3D.cpp:964-965)"""
     return np.tan(np.ascontiguousarray(slope_deg, np.float32).astype(np.float64) * DEG_TO_RAD).astype(np.float32)
+
+
+# ---- the same preparation on the GPU (include/sf3d_gis.h, criteria3d_b200/csrc/sf3d_gis.cu) ------------------------
+def prepare_on_device(dem: np.ndarray, cell: float, nodata: float = -9999.0):
+    """slope [deg], aspect [deg], runoff-boundary mask and tan(slope) of a DEM in one call of the product's
+    sf3d_gis_slope_aspect_boundary (one CUDA thread per cell).  Fails loudly when the CUDA library is missing or no
+    device is present: there is no CPU fallback (slope_aspect / boundary_runoff above are the host restatement the
+    tests pin against the reference's own gis code)."""
+    import ctypes
+    from .capi import PRODUCT_LIB
+    if not PRODUCT_LIB.exists():
+        raise RuntimeError(f"{PRODUCT_LIB} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` first")
+    lib = ctypes.CDLL(str(PRODUCT_LIB))
+    fn = lib.sf3d_gis_slope_aspect_boundary
+    fp, up = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_uint8)
+    fn.restype = ctypes.c_uint8
+    fn.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_double, ctypes.c_float, fp, fp, fp, up, fp]
+    z = np.ascontiguousarray(dem, np.float32)
+    rows, cols = z.shape
+    slope = np.empty_like(z); aspect = np.empty_like(z); tan = np.empty_like(z)
+    mask = np.empty(z.shape, np.uint8)
+    rc = fn(rows, cols, float(cell), np.float32(nodata), z.ctypes.data_as(fp), slope.ctypes.data_as(fp), aspect.ctypes.data_as(fp),
+            mask.ctypes.data_as(up), tan.ctypes.data_as(fp))
+    if rc != 0:
+        raise RuntimeError(f"sf3d_gis_slope_aspect_boundary returned {rc} (2 = no CUDA device / allocation failed, 6 = bad raster)")
+    return slope, aspect, mask, tan

@@ -61,9 +61,16 @@ def _raster_slope_and_outlet(dem: np.ndarray, valid: np.ndarray, cell: float):
     gis::computeSlopeAspectMaps, Project3D::setLateralBoundary (gis::isBoundaryRunoff) and the
     tan(slope) of Project3D::setCrit3DTopography, restated in criteria3d_b200/raster.py and pinned bit for bit
     against the reference's own gis code (tests/test_raster.py)."""
-    from .raster import boundary_runoff, boundary_slope_tan, slope_aspect
+    from .raster import boundary_runoff, boundary_slope_tan, prepare_on_device, slope_aspect
     nodata = -9999.0
     z = np.where(valid, dem, np.float32(nodata)).astype(np.float32)
+    import torch
+    if torch.cuda.is_available():
+        # on a GPU box the maps come from the product's device kernel (include/sf3d_gis.h), bit-identical to the host
+        # restatement on every test raster (tests/test_gpu_raster_prep.py)
+        _, _, outlet, tan_all = prepare_on_device(z, cell, nodata)
+        tan = np.where(valid, tan_all, np.float32(0.0)).astype(np.float32)
+        return np.ascontiguousarray(tan), np.ascontiguousarray(outlet)
     slope_deg, aspect = slope_aspect(z, cell, nodata)
     tan = np.where(valid, boundary_slope_tan(slope_deg), np.float32(0.0)).astype(np.float32)
     return np.ascontiguousarray(tan), np.ascontiguousarray(boundary_runoff(z, aspect, nodata))

@@ -64,3 +64,12 @@ def test_product_does_not_link_or_reference_the_oracle():
         if src.suffix in (".cu", ".cpp", ".h", ".py"):
             text = src.read_text()
             assert not any(t in text for t in tokens), src
+
+
+def test_raster_preparation_symbol_exported():
+    """include/sf3d_gis.h: declared symbols are exported by the product (no compute call here)"""
+    hdr = (ROOT / "include" / "sf3d_gis.h").read_text()
+    declared = sorted(set(re.findall(r"\b(sf3d_gis_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared == ["sf3d_gis_slope_aspect_boundary"]
+    h = ctypes.CDLL(str(PRODUCT_LIB), mode=ctypes.RTLD_LOCAL)
+    assert all(hasattr(h, s) for s in declared)
