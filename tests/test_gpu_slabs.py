@@ -25,7 +25,7 @@ def _torchrun(world, port, *args, env_extra=None, timeout=900):
     return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
 
 
-@pytest.mark.parametrize("world,heat", [(2, False), (4, False), (2, True)])
+@pytest.mark.parametrize("world,heat", [(2, False), (4, False), (8, False), (2, True)])
 def test_slabs_match_oracle(world, heat):
     r = _torchrun(world, 29600 + world + (10 if heat else 0), *(["--heat"] if heat else []))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
