@@ -253,6 +253,8 @@ _EXT = [
     ("sf3d_ext_build_grid", u8, [C.POINTER(GridDesc)]),
     ("sf3d_ext_set_forcing_rasters", u8, [C.POINTER(ForcingDesc)]),
     ("sf3d_ext_get_layer_rasters", u8, [C.c_int, u32, u32, C.c_float, C.POINTER(C.c_float)]),
+    ("sf3d_ext_get_layer_rasters_async", u8, [C.c_int, u32, u32, C.c_float, C.POINTER(C.c_float)]),
+    ("sf3d_ext_wait_rasters", u8, []),
     ("sf3d_ext_set_fixed_temperature", u8, [u32, u32, C.POINTER(dbl), dbl]),
     ("sf3d_ext_get_counters", u8, [C.POINTER(Counters)]),
     ("sf3d_ext_reset_counters", u8, []),
@@ -370,6 +372,19 @@ class SoilFluxes3D:
         if rc:
             raise RuntimeError(f"sf3d_ext_get_layer_rasters -> {SF3Derror(rc).name}")
         return out
+
+    def get_layer_rasters_async(self, field: int, first_layer: int, n_layers: int, shape, out: np.ndarray, nodata: float = -9999.0) -> None:
+        """The same maps, copied to `out` (page-locked float32 [n_layers, rows, cols]) while later calls run; read `out`
+        only after wait_rasters()."""
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.size == n_layers * shape[0] * shape[1]
+        rc = self.lib.sf3d_ext_get_layer_rasters_async(int(field), first_layer, n_layers, nodata, _ptr(out, C.c_float))
+        if rc:
+            raise RuntimeError(f"sf3d_ext_get_layer_rasters_async -> {SF3Derror(rc).name}")
+
+    def wait_rasters(self) -> None:
+        rc = self.lib.sf3d_ext_wait_rasters()
+        if rc:
+            raise RuntimeError(f"sf3d_ext_wait_rasters -> {SF3Derror(rc).name}")
 
     def set_fixed_temperature(self, first: int, temperature: np.ndarray, depth: float) -> int:
         t = np.ascontiguousarray(temperature, dtype=np.float64)

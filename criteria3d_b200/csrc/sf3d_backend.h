@@ -21,6 +21,12 @@ void   dev_fill_f64(double *p, size_t n, double value);
 void   dev_copy(void *dst, const void *src, size_t bytes);      // device to device
 void   h2d(void *dst, const void *src, size_t bytes);
 void   d2h(void *dst, const void *src, size_t bytes);
+// overlapped device-to-host copy (second stream): the copy starts after everything enqueued on the library's stream so far and
+// runs beside later work; `slot` (0 / 1) names the staging buffer it reads, so that overlap_acquire(slot) can make the library's
+// stream wait for that copy before the buffer is written again
+void   overlap_acquire(int slot);
+void   d2h_overlapped(void *dst, const void *src, size_t bytes, int slot);
+void   overlap_sync();
 void  *pinned_alloc(size_t bytes);
 void   pinned_free(void *p);
 void   dev_sync();

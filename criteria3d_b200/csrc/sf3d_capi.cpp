@@ -78,6 +78,7 @@ struct State {
            *scratch = nullptr;
     uint32_t *mcol = nullptr;
     uint16_t *pid = nullptr; int32_t *pattern = nullptr; bool patternsOk = false;
+    void *overlapStage[2] = {nullptr, nullptr}; size_t overlapStageBytes[2] = {0, 0}; int overlapSlot = 0;
     uint32_t hotPid = 0; int32_t hotOff[SF3D_NLINK] = {0};
     Ctrl *ctrl = nullptr;
     // raster side of a graph built by sf3d_ext_build_grid (kept for the raster-facing forcing / output calls)
@@ -1156,7 +1157,7 @@ uint8_t sf3d_ext_set_forcing_rasters(const sf3d_forcing_desc *f)
     }, (uint8_t)SF3D_MEMORY_ERROR);
 }
 
-uint8_t sf3d_ext_get_layer_rasters(int field, uint32_t firstLayer, uint32_t nLayers, float nodata, float *dst)
+static uint8_t layer_rasters(int field, uint32_t firstLayer, uint32_t nLayers, float nodata, float *dst, bool overlapped)
 {
     return guarded([&]() -> uint8_t {
         REQUIRE_INIT_E();
@@ -1174,13 +1175,36 @@ uint8_t sf3d_ext_get_layer_rasters(int field, uint32_t firstLayer, uint32_t nLay
         }
         uint8_t rc = sync_to_device();
         if (rc) return rc;
-        const size_t cells = (size_t)S.raster.rows * S.raster.cols;
-        float *stage = (float *)raster_stage(cells * nLayers * sizeof(float));
+        const size_t cells = (size_t)S.raster.rows * S.raster.cols, bytes = cells * nLayers * sizeof(float);
+        float *stage;
+        int slot = 0;
+        if (overlapped)
+        {
+            // two staging buffers of their own (the forcing upload uses the shared one): a copy may still be reading one of
+            // them while the next maps are written into the other
+            slot = S.overlapSlot ^= 1;
+            if (S.overlapStageBytes[slot] < bytes)
+            {
+                overlap_sync();
+                dev_free(S.overlapStage[slot]); S.overlapStage[slot] = nullptr; S.overlapStageBytes[slot] = 0;
+                S.overlapStage[slot] = dev_alloc(bytes); S.overlapStageBytes[slot] = bytes;
+            }
+            overlap_acquire(slot);
+            stage = (float *)S.overlapStage[slot];
+        }
+        else stage = (float *)raster_stage(bytes);
         for (uint32_t l = 0; l < nLayers; ++l) k_layer_raster(S.eng.v, S.raster, field, firstLayer + l, nodata, stage + (size_t)l * cells);
-        d2h(dst, stage, cells * nLayers * sizeof(float));
+        if (overlapped) d2h_overlapped(dst, stage, bytes, slot);
+        else d2h(dst, stage, bytes);
         return SF3D_OK;
     }, (uint8_t)SF3D_MEMORY_ERROR);
 }
+uint8_t sf3d_ext_get_layer_rasters(int field, uint32_t firstLayer, uint32_t nLayers, float nodata, float *dst)
+{ return layer_rasters(field, firstLayer, nLayers, nodata, dst, false); }
+uint8_t sf3d_ext_get_layer_rasters_async(int field, uint32_t firstLayer, uint32_t nLayers, float nodata, float *dst)
+{ return layer_rasters(field, firstLayer, nLayers, nodata, dst, true); }
+uint8_t sf3d_ext_wait_rasters(void)
+{ return guarded([&]() -> uint8_t { overlap_sync(); return SF3D_OK; }, (uint8_t)SF3D_MEMORY_ERROR); }
 
 uint8_t sf3d_ext_set_fixed_temperature(uint32_t first, uint32_t count, const double *temperature, double depth)
 {

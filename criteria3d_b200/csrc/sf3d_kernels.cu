@@ -137,6 +137,32 @@ void h2d(void *dst, const void *src, size_t bytes)
 { ensure_device(); CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_stream)); CUDA_OK(cudaStreamSynchronize(g_stream)); }
 void d2h(void *dst, const void *src, size_t bytes)
 { ensure_device(); CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_stream)); CUDA_OK(cudaStreamSynchronize(g_stream)); }
+static cudaStream_t g_copyStream = nullptr;
+static cudaEvent_t g_evReady = nullptr, g_evCopied[2] = {nullptr, nullptr};
+static bool g_slotUsed[2] = {false, false};
+static void ensure_copy_stream()
+{
+    ensure_device();
+    if (g_copyStream) return;
+    CUDA_OK(cudaStreamCreateWithFlags(&g_copyStream, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreateWithFlags(&g_evReady, cudaEventDisableTiming));
+    for (int k = 0; k < 2; ++k) CUDA_OK(cudaEventCreateWithFlags(&g_evCopied[k], cudaEventDisableTiming));
+}
+void overlap_acquire(int slot)
+{
+    ensure_copy_stream();
+    if (g_slotUsed[slot]) CUDA_OK(cudaStreamWaitEvent(g_stream, g_evCopied[slot], 0));
+}
+void d2h_overlapped(void *dst, const void *src, size_t bytes, int slot)
+{
+    ensure_copy_stream();
+    CUDA_OK(cudaEventRecord(g_evReady, g_stream));
+    CUDA_OK(cudaStreamWaitEvent(g_copyStream, g_evReady, 0));
+    CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_copyStream));
+    CUDA_OK(cudaEventRecord(g_evCopied[slot], g_copyStream));
+    g_slotUsed[slot] = true;
+}
+void overlap_sync() { if (g_copyStream) CUDA_OK(cudaStreamSynchronize(g_copyStream)); }
 void *pinned_alloc(size_t bytes) { ensure_device(); void *p = nullptr; CUDA_OK(cudaMallocHost(&p, bytes)); return p; }
 void pinned_free(void *p) { if (p) cudaFreeHost(p); }
 void dev_sync() { ensure_device(); CUDA_OK(cudaStreamSynchronize(g_stream)); }

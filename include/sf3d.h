@@ -261,6 +261,14 @@ uint8_t sf3d_ext_set_forcing_rasters(const sf3d_forcing_desc *desc);
  * [mm] (:1936-1940).  dst is a HOST buffer of n_layers*rows*cols floats. */
 uint8_t sf3d_ext_get_layer_rasters(int field, uint32_t first_layer, uint32_t n_layers, float nodata, float *dst);
 
+/* The same maps without blocking the caller (product: the maps are written into a device staging buffer in stream order,
+ * i.e. they are the state after every step computed so far, and copied to dst on a second stream while later sf3d_* calls
+ * -- the next computeStep -- run; dst should be page-locked host memory, otherwise the copy is staged by the driver and may not
+ * overlap).  dst must not be read before sf3d_ext_wait_rasters() has returned; at most two copies are in flight, a third call waits
+ * on the device for the oldest.  CPU libraries: the synchronous call, and a no-op wait. */
+uint8_t sf3d_ext_get_layer_rasters_async(int field, uint32_t first_layer, uint32_t n_layers, float nodata, float *dst);
+uint8_t sf3d_ext_wait_rasters(void);
+
 /* setNodeBoundaryFixedTemperature(i, T[k], depth) for nodes [first, first+count) */
 uint8_t sf3d_ext_set_fixed_temperature(uint32_t first, uint32_t count, const double *temperature, double depth);
 
