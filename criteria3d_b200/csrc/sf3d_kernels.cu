@@ -137,6 +137,15 @@ void h2d(void *dst, const void *src, size_t bytes)
 { ensure_device(); CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_stream)); CUDA_OK(cudaStreamSynchronize(g_stream)); }
 void d2h(void *dst, const void *src, size_t bytes)
 { ensure_device(); CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_stream)); CUDA_OK(cudaStreamSynchronize(g_stream)); }
+const void *host_alias(const void *hostPtr)
+{
+    ensure_device();
+    static const bool off = getenv("SF3D_NO_MAPPED_FORCING") != nullptr;
+    if (off || !hostPtr) return nullptr;
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, hostPtr) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return (a.type == cudaMemoryTypeHost) ? a.devicePointer : nullptr;
+}
 static cudaStream_t g_copyStream = nullptr;
 static cudaEvent_t g_evReady = nullptr, g_evCopied[2] = {nullptr, nullptr};
 static bool g_slotUsed[2] = {false, false};
@@ -1551,6 +1560,10 @@ void k_update_conductance(const SF3DView &v) { ProfScope ps(SF3D_K_OTHER); kern_
 void k_save_water_fluxes(const SF3DView &v, double dtHeat, double dtWater)
 {
     { ProfScope ps(SF3D_K_HEAT_COEFFS); kern_heat_coeffs<<<GRID(v.N)>>>(v, dtHeat, dtWater); LAUNCH_CHECK(); }
+    // Heat::saveNodeWaterFluxes (heat.cpp:109-138).  The snapshot is read by the advective terms only (computeAdvectiveFlux,
+    // heat.cpp:606-621; boundary advection :273-287) and, in save mode All, by the per-type flux getters: without either the
+    // pass has no observer and is not run (the reference computes it regardless)
+    if (!(v.computeHeatAdvection || v.hfSaveMode == 2)) return;
     ProfScope ps(SF3D_K_HEAT_FLUX_SNAPSHOT);
     kern_save_water_fluxes<<<GRID(v.N)>>>(v, dtHeat, dtWater); LAUNCH_CHECK();
 }
