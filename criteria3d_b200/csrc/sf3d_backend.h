@@ -27,8 +27,6 @@ void   d2h(void *dst, const void *src, size_t bytes);
 void   overlap_acquire(int slot);
 void   d2h_overlapped(void *dst, const void *src, size_t bytes, int slot);
 void   overlap_sync();
-// device-visible alias of a page-locked host buffer (unified addressing), or nullptr for pageable memory
-const void *host_alias(const void *hostPtr);
 void  *pinned_alloc(size_t bytes);
 void   pinned_free(void *p);
 void   dev_sync();

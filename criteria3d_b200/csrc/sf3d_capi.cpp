@@ -1144,22 +1144,15 @@ uint8_t sf3d_ext_set_forcing_rasters(const sf3d_forcing_desc *f)
         if (rc) return rc;
         const size_t cells = (size_t)f->rows * f->cols;
         const size_t nPrec = f->precipitation ? cells : 0, nSink = f->layer_sink ? cells * f->n_sink_layers : 0;
-        // Page-locked maps are read by the kernel where they lie (mapped host memory, 4 B per cell over PCIe, no copy engine: an
-        // output-map download still in flight on the copy stream does not delay them); pageable maps are staged through a copy.
-        const float *dPrec = nPrec ? (const float *)host_alias(f->precipitation) : nullptr;
-        const float *dSink = nSink ? (const float *)host_alias(f->layer_sink) : nullptr;
-        const size_t stagedPrec = (nPrec && !dPrec) ? nPrec : 0, stagedSink = (nSink && !dSink) ? nSink : 0;
-        float *stage = (stagedPrec + stagedSink) ? (float *)raster_stage((stagedPrec + stagedSink + 1) * sizeof(float)) : nullptr;
+        float *stage = (float *)raster_stage((nPrec + nSink + 1) * sizeof(float));
         ForcingDev fd{};
-        if (stagedPrec) { h2d(stage, f->precipitation, nPrec * sizeof(float)); dPrec = stage; }
-        if (stagedSink) { h2d(stage + stagedPrec, f->layer_sink, nSink * sizeof(float)); dSink = stage + stagedPrec; }
-        fd.precipitation = dPrec; fd.layerSink = dSink;
+        if (nPrec) { h2d(stage, f->precipitation, nPrec * sizeof(float)); fd.precipitation = stage; }
+        if (nSink) { h2d(stage + nPrec, f->layer_sink, nSink * sizeof(float)); fd.layerSink = stage + nPrec; }
         fd.precipitationNodata = f->precipitation_nodata; fd.sinkNodata = f->sink_nodata;
         fd.nSinkLayers = f->n_sink_layers; fd.accumulate = f->accumulate;
         S.sink.push();
         k_forcing_rasters(S.eng.v, S.raster, fd);
         S.sink.dev_written();
-        if ((nPrec && !stagedPrec) || (nSink && !stagedSink)) dev_sync();      // the caller's buffers are free again on return
         return SF3D_OK;
     }, (uint8_t)SF3D_MEMORY_ERROR);
 }

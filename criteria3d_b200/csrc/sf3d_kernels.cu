@@ -137,15 +137,6 @@ void h2d(void *dst, const void *src, size_t bytes)
 { ensure_device(); CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_stream)); CUDA_OK(cudaStreamSynchronize(g_stream)); }
 void d2h(void *dst, const void *src, size_t bytes)
 { ensure_device(); CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_stream)); CUDA_OK(cudaStreamSynchronize(g_stream)); }
-const void *host_alias(const void *hostPtr)
-{
-    ensure_device();
-    static const bool off = getenv("SF3D_NO_MAPPED_FORCING") != nullptr;
-    if (off || !hostPtr) return nullptr;
-    cudaPointerAttributes a{};
-    if (cudaPointerGetAttributes(&a, hostPtr) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    return (a.type == cudaMemoryTypeHost) ? a.devicePointer : nullptr;
-}
 static cudaStream_t g_copyStream = nullptr;
 static cudaEvent_t g_evReady = nullptr, g_evCopied[2] = {nullptr, nullptr};
 static bool g_slotUsed[2] = {false, false};
@@ -167,8 +158,7 @@ void d2h_overlapped(void *dst, const void *src, size_t bytes, int slot)
     ensure_copy_stream();
     CUDA_OK(cudaEventRecord(g_evReady, g_stream));
     CUDA_OK(cudaStreamWaitEvent(g_copyStream, g_evReady, 0));
-    // in pieces: a host-to-device upload issued meanwhile on the library's stream (the next forcing map) then waits for one
-    // piece at most instead of for the whole download (measured: 0.8 ms per step of exposed upload behind a 46 MB copy)
+    // in pieces, so that small copies of the library's stream (the control block after every batch of sweeps) can interleave
     const size_t piece = (size_t)4 << 20;
     for (size_t off = 0; off < bytes; off += piece)
         CUDA_OK(cudaMemcpyAsync((char *)dst + off, (const char *)src + off, (bytes - off < piece) ? bytes - off : piece,

@@ -32,22 +32,3 @@ def test_async_maps_equal_sync_maps_while_the_next_steps_run(product):
     product.wait_rasters()
     assert np.array_equal(out, product.get_layer_rasters(Field.WATER_CONTENT, 0, cat.layers, shape))
 
-
-def test_page_locked_forcing_maps_are_read_in_place_with_the_same_result(product):
-    """sf3d_ext_set_forcing_rasters reads page-locked maps where they lie (mapped host memory) and stages pageable ones:
-    the assembled sink / source must be the same"""
-    cat = Catchment(64, 48, 4)
-    setup(product, cat)
-    rng = np.random.default_rng(3)
-    rain = (rng.random((cat.rows, cat.cols)) * 30).astype(np.float32)
-    rain[5, 7] = -9999
-    sink = (rng.random((cat.layers, cat.rows, cat.cols)) * 0.4).astype(np.float32)
-    assert product.set_forcing_rasters(precipitation=rain, layer_sink=sink) == 0
-    want = product.get_field(Field.WATER_SINK_SOURCE, 0, cat.n_nodes)
-    assert product.set_forcing_rasters(precipitation=np.zeros_like(rain)) == 0          # something else in between
-    rain_p = torch.from_numpy(rain).pin_memory().numpy()
-    sink_p = torch.from_numpy(sink).pin_memory().numpy()
-    assert product.set_forcing_rasters(precipitation=rain_p, layer_sink=sink_p) == 0
-    rain_p[:] = 0                                                                         # the call has consumed the buffers
-    got = product.get_field(Field.WATER_SINK_SOURCE, 0, cat.n_nodes)
-    assert np.array_equal(got, want) and np.any(want > 0) and np.any(want < 0)
