@@ -437,6 +437,7 @@ def main():
                     "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
                     "ms_per_step": r["ms_e2e"] / args.steps, "same_steps_as_value": r["same_steps"], "sweeps": int(sweeps_e2e),
                     "host_ms_per_step": {"forcing_upload": r["host_ms"][0], "compute_step": r["host_ms"][1], "result_download_exposed": r["host_ms"][2]},
+                    "host_ms_note": "computeStep returns with its accept pass (0.6 ms) still enqueued: the next host-blocking call, the forcing upload, waits for it",
                     "result_download": "sf3d_ext_get_layer_rasters_async into two page-locked buffers: the copy of step k overlaps the kernels of step k + 1 "
                                        "(second CUDA stream); the host waits for it and reads the maps before the next download is issued, the last one "
                                        "inside the timed region",
