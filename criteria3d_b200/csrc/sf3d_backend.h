@@ -60,6 +60,8 @@ void k_link_geometry(const SF3DView &v, int *surfaceOrderOk);
 void k_heat_geometry(const SF3DView &v);       // static per-node pressure and per-link 3-D distance
 bool k_build_patterns(const SF3DView &v, uint16_t *pid, int32_t *table, uint32_t *hotPid, int32_t hotOff[SF3D_NLINK]);   // pattern-compressed column indices
 size_t pattern_table_bytes();
+bool k_jacobi_persistent_ok(const SF3DView &v);     // small graphs: all sweeps of a solve in one cooperative launch
+void k_jacobi_persistent(const SF3DView &v, double *xa, double *xb, int maxIter, double tol);
 void k_begin_try(const SF3DView &v);
 void k_restore_old(const SF3DView &v);
 void k_node_phase(const SF3DView &v, double dt, int withCapacity);

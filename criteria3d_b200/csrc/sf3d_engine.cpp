@@ -250,7 +250,13 @@ int Engine::solveWater(int approx)
     int launched = 0;
     Ctrl c{};
     int batch = std::min(std::max(lastSweeps + 1, 4), 32);
-    for (;;)
+    if (k_jacobi_persistent_ok(v))
+    {
+        // small graph: the whole solve is one launch and one control-block read
+        k_jacobi_persistent(v, xbuf(start), xbuf(start ^ 1), maxIter, p->residualTolerance);
+        read_ctrl(v, &c);
+    }
+    else for (;;)
     {
         const int n = std::min(batch, maxIter - launched);
         for (int k = 0; k < n; ++k, ++launched)

@@ -15,6 +15,7 @@
 //     batch of sweeps can be enqueued without synchronising; sweeps launched after convergence
 //     return immediately.
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <dlfcn.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -605,6 +606,57 @@ __global__ void __launch_bounds__(SF3D_BLOCK, SF3D_JACOBI_BLOCKS) kern_jacobi(SF
             v.ctrl->ticket = 0;
         }
     }
+}
+
+// ---- small graphs: all sweeps of one solve in ONE launch -------------------------------------------------
+// A catchment of a few ten thousand nodes (BASELINE config 1, CRITERIA-1D-sized callers) sweeps in ~1 us, so a solve of
+// 30 sweeps is bound by 30 launches and by the batches' control-block reads.  This kernel is launched cooperatively
+// (every block resident) and iterates on the device: sweep, block partial, grid-wide barrier, EVERY block folds the
+// partials in the same fixed order and applies the stopping rule of cpusolver.cpp:678-700 to its own copy of the
+// solver state, so all blocks leave the loop in the same sweep without a second barrier; the partials alternate
+// between two arrays, so a fast block's next partial never lands in the array a slow block is still folding.  Grid
+// size, thread -> row mapping, partial sums and fold order are those of kern_jacobi: the residual norms, and with them
+// the decisions, are bit-identical to the launch-per-sweep path.  xa holds the solution at entry.
+__global__ void __launch_bounds__(SF3D_BLOCK, SF3D_JACOBI_BLOCKS) kern_jacobi_persistent(SF3DView v, double *xa, double *xb, int maxIter, double tol)
+{
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    Ctrl *c = v.ctrl;
+    if (c->status != SOLVE_RUNNING) return;             // Courant failure of the assembly: the same branch in every block
+    __shared__ double sh[SF3D_BLOCK / 32];
+    __shared__ int shStatus;
+    double best = c->bestNorm, curr = 0.;               // thread 0's copy of the solver state (identical in every block)
+    int sweeps = 0, status = SOLVE_RUNNING;
+    for (;;)
+    {
+        const double *xin = (sweeps & 1) ? xb : xa;
+        double *xout = (sweeps & 1) ? xa : xb;
+        double *part = (sweeps & 1) ? v.partB : v.partA;
+        double norm = 0.;
+        for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
+            norm += sf3d_row_jacobi_coherent(v, i, xin, xout);
+        norm = block_reduce<false>(norm, sh);
+        if (threadIdx.x == 0) part[blockIdx.x] = norm;
+        grid.sync();
+        const double total = fold_partials<false>(part, sh);
+        ++sweeps;
+        if (threadIdx.x == 0)
+        {
+            curr = total / v.nGlobal;                                       // water.cpp:600
+            int st = SOLVE_RUNNING;
+            if (curr < tol) st = SOLVE_CONVERGED;                           // cpusolver.cpp:692
+            else if (curr > best * 10) st = SOLVE_DIVERGED;                 // :695
+            else
+            {
+                if (curr < best) best = curr;                               // :698
+                if (sweeps >= maxIter) st = SOLVE_MAXITER;
+            }
+            shStatus = st;
+        }
+        __syncthreads();
+        status = shStatus;
+        if (status != SOLVE_RUNNING) break;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { c->lastNorm = curr; c->sweeps = sweeps; c->bestNorm = best; c->status = status; }
 }
 
 // halo exchange helpers: gather owned boundary values into a send buffer / scatter received ones
@@ -1479,6 +1531,33 @@ void k_assemble(const SF3DView &v, double dt, int approx, double dtMin)
         comm_allreduce(v.ctrl->red, 1, true, v.ctrl);
         kern_rule_courant<<<1, 1, 0, g_stream>>>(v.ctrl, dt, dtMin); LAUNCH_CHECK();
     }
+}
+// the persistent solve is used for graphs one grid covers with one row per thread (beyond that a sweep takes much longer
+// than a launch and the launch-per-sweep path overlaps its control reads with queued sweeps); SF3D_PERSISTENT_SOLVE=0
+// disables it, =N sets the node limit
+bool k_jacobi_persistent_ok(const SF3DView &v)
+{
+    static int maxCoopBlocks = -1;
+    if (maxCoopBlocks < 0)
+    {
+        ensure_device();
+        int coop = 0, perSm = 0, sms = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, g_device);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g_device);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern_jacobi_persistent, SF3D_BLOCK, 0) != cudaSuccess) { cudaGetLastError(); perSm = 0; }
+        maxCoopBlocks = coop ? perSm * sms : 0;
+    }
+    const char *e = getenv("SF3D_PERSISTENT_SOLVE");        // read per solve: tests switch it inside one process
+    const long limit = e ? atol(e) : (long)SF3D_MAX_BLOCKS * SF3D_BLOCK;
+    return v.world == 1 && (long)v.N <= limit && reduce_blocks(v.N) <= maxCoopBlocks;
+}
+void k_jacobi_persistent(const SF3DView &v, double *xa, double *xb, int maxIter, double tol)
+{
+    ProfScope ps(SF3D_K_JACOBI);
+    SF3DView vv = v;
+    void *args[] = {(void *)&vv, (void *)&xa, (void *)&xb, (void *)&maxIter, (void *)&tol};
+    CUDA_OK(cudaLaunchCooperativeKernel((const void *)kern_jacobi_persistent, dim3(reduce_blocks(v.N)), dim3(SF3D_BLOCK), args, 0, g_stream));
+    LAUNCH_CHECK();
 }
 void k_jacobi(const SF3DView &v, const double *xin, double *xout, int maxIter, double tol)
 {
