@@ -388,6 +388,13 @@ __global__ void __launch_bounds__(SF3D_BLOCK, SF3D_NODE_BLOCKS) kern_node_phase(
 
 // ---- row-slab ranks: device side of the peer-memory all-reduce ---------------------------------------
 // Every rank owns a mailbox that all ranks can write through CUDA IPC (NVLink peer stores).
+// SF3D_MULTI_DEBUG timing switches of the fused multi-GPU sweep (profiles/r02_fused_sweep_breakdown.md): compiled in only with
+// -DSF3D_TIMING_SWITCHES; the product build has none of them
+#ifdef SF3D_TIMING_SWITCHES
+#define SF3D_DBG(flags, bit) (((flags) & (bit)) != 0)
+#else
+#define SF3D_DBG(flags, bit) false
+#endif
 #define SF3D_MAX_RANKS 16
 // One 8-byte mailbox word carries 32 bits of payload and a 32-bit tag derived from the sequence number: an aligned
 // 8-byte store is single-copy atomic, also over NVLink, so a reader that sees the expected tag has the payload of
@@ -482,7 +489,7 @@ __device__ __forceinline__ void last_block_allreduce(const CommDev &cm, Ctrl *c,
     if (threadIdx.x < 32)
     {
         const unsigned long long t0 = global_ns();
-        if (!(cm.dbg & 8)) p2p_allreduce_warp(cm, count, isMax, c->red, c);
+        if (!SF3D_DBG(cm.dbg, 8)) p2p_allreduce_warp(cm, count, isMax, c->red, c);
         if (threadIdx.x == 0) { c->commNs += global_ns() - t0; c->commCount += 1ull; }
     }
     __syncthreads();
@@ -703,8 +710,8 @@ __global__ void __launch_bounds__(SF3D_BLOCK, SF3D_JACOBI_BLOCKS) kern_jacobi_mu
     // (boundary row k goes to thread k / gridDim.x of block k % gridDim.x: every block takes the same share in its
     // lowest warps, so no block starts its interior rows a whole dependent-load chain later than the others;
     // measured against "one row per thread of the last blocks": 6.5 us per sweep)
-    for (uint32_t k = ((e.dbg & 16) ? (gridDim.x - 1u - blockIdx.x) * SF3D_BLOCK + threadIdx.x : threadIdx.x * gridDim.x + blockIdx.x);
-         k < ((e.dbg & 4) ? 0u : e.nBoundary); k += gridDim.x * SF3D_BLOCK)
+    for (uint32_t k = (SF3D_DBG(e.dbg, 16) ? (gridDim.x - 1u - blockIdx.x) * SF3D_BLOCK + threadIdx.x : threadIdx.x * gridDim.x + blockIdx.x);
+         k < (SF3D_DBG(e.dbg, 4) ? 0u : e.nBoundary); k += gridDim.x * SF3D_BLOCK)
     {
         const uint32_t i = e.bIdx[k];
         double xn;
@@ -715,16 +722,16 @@ __global__ void __launch_bounds__(SF3D_BLOCK, SF3D_JACOBI_BLOCKS) kern_jacobi_mu
         {
             if (p >= e.nPeers) break;
             const uint32_t r = e.remote[p][k];
-            if (r != SF3D_NO_REMOTE && !(e.dbg & 1)) e.peerX[p][r] = xn;
+            if (r != SF3D_NO_REMOTE && !SF3D_DBG(e.dbg, 1)) e.peerX[p][r] = xn;
         }
         // system-scope fence by the threads that stored into peer memory, right here (early in the kernel, behind
         // other warps' work): these stores are then ordered before this block's ticket below and, through the last
         // block's own fence, before the sequence number the peers wait for
-        if (!(e.dbg & 2)) __threadfence_system();
+        if (!SF3D_DBG(e.dbg, 2)) __threadfence_system();
     }
     for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
     {
-        if ((e.dbg & 4) ? (v.pid[i] == SF3D_GHOST_PID) : ((v.pid[i] & SF3D_PID_SKIP) != 0)) continue;         // ghost row, or boundary row already done above
+        if (SF3D_DBG(e.dbg, 4) ? (v.pid[i] == SF3D_GHOST_PID) : ((v.pid[i] & SF3D_PID_SKIP) != 0)) continue;         // ghost row, or boundary row already done above
         const double d = HEAT ? sf3d_row_heat_jacobi(v, i, xin, xout) : sf3d_row_jacobi(v, i, xin, xout);
         norm = HEAT ? ((norm < d) ? d : norm) : (norm + d);
     }
