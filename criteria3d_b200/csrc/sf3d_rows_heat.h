@@ -300,7 +300,14 @@ SF3D_HD double sf3d_heat_node_water(const SF3DView &v, uint32_t i, const SoilRec
         const double theta = (h >= 0.) ? s.thetaS : sf3d_theta_from_se(s, Se);
         const HeatNodeCtx c = h_node_ctx(s, T, h, theta);
         K += h_ivk(c) * (HC_GRAVITY / HC_WATER_DENSITY);
+#ifdef SF3D_DEVICE_MATH
+        // the only reader of this pair is the thermal invariant flux of the water rows, which divides the vapour flux by the
+        // water density (water.cpp:337): the mean is homogeneous of degree 1, so the division is done once per node here
+        // instead of once per link there
+        h_pair_store(v.hTVK, i, h_tvk(s, c, v.hPress[i]) * (1. / HC_WATER_DENSITY));
+#else
         h_pair_store(v.hTVK, i, h_tvk(s, c, v.hPress[i]));
+#endif
         if (dThetadH)
         {
             const double dThetaVdPsi = (c.svc * c.rh / HC_WATER_DENSITY) * ((s.thetaS - theta) * HC_MH2O / (HC_R_GAS * T) - *dThetadH / HC_GRAVITY);
@@ -364,9 +371,16 @@ SF3D_HD double sf3d_heat_thermal_invariant(const SF3DView &v, uint32_t i, int sl
                                           const SF3DPair tlj, const SF3DPair tvj, double tmj)
 {
     const double dT = tmj - tmi;
+#ifdef SF3D_DEVICE_MATH
+    const double zeta = h_link_zeta(v, i, slot);                // one load for both fluxes; tv pairs are stored / rho_w
+    double f = (h_pair_mean(tli, tlj) * dT) * zeta;
+    if (v.computeHeatVapor) f += (h_pair_mean(tvi, tvj) * dT) * zeta;
+    return f;
+#else
     double f = h_link_flux(v, i, slot, h_pair_mean(tli, tlj) * dT);
     if (v.computeHeatVapor) f += h_link_flux(v, i, slot, h_pair_mean(tvi, tvj) * dT) / HC_WATER_DENSITY;
     return f;
+#endif
 }
 
 // one soil row's invariant fluxes of the water system: thermal liquid (+ thermal vapour / rho_w) flux of every
@@ -728,9 +742,16 @@ SF3D_HD void sf3d_row_heat_assemble(const SF3DView &v, uint32_t i, double dtHeat
     double b = v.cap[i] * v.oldT[i] / dtHeat - heatCapacity / dtHeat + v.hFlux[i] + invariant + sumF0;
     if (diag > 0)
     {
+#ifdef SF3D_DEVICE_MATH
+        const double inv = 1. / diag;                   // one division per row instead of eleven
+        b *= inv;
+        #pragma unroll 1
+        for (int slot = 0; slot < SF3D_NLINK; ++slot) val[slot] *= inv;
+#else
         b /= diag;
         #pragma unroll 1
         for (int slot = 0; slot < SF3D_NLINK; ++slot) val[slot] /= diag;
+#endif
     }
     #pragma unroll 1
     for (int slot = 0; slot < SF3D_NLINK; ++slot) v.mval[(size_t)slot * N + i] = val[slot];
