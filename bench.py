@@ -364,7 +364,7 @@ def main():
 
     sf = load_product()
     assert sf.set_device(local_rank) == 0
-    parity = None
+    parity = parity_c4 = None
     if world > 1:
         from criteria3d_b200.mgpu import wire_ranks
         wire_ranks(sf, rank, world)
@@ -373,6 +373,8 @@ def main():
             sys.path.insert(0, str(ROOT / "tests"))
             from mgpu_slab_check import reduce_over_ranks, slab_parity
             parity = reduce_over_ranks(slab_parity(sf, rank, world))
+            # ... and the C4 recipe (20 soil layers, saturated lower third, free drainage) at small size
+            parity_c4 = reduce_over_ranks(slab_parity(sf, rank, world, c4=True)) if not args.no_c4 else None
 
     # weak scaling: every GPU owns a rows x cols slab of a (world * rows) x cols catchment
     r = run_workload(sf, args, (args.rows, args.cols, args.soil_layers), rank, local_rank, world, args.steps, warmup,
@@ -486,6 +488,8 @@ def main():
                 "kernel_ms": {k: round(v["ms"], 3) for k, v in c4["ktimes"].items() if v["ms"] > 0},
                 "clocks": c4["clocks"],
             }
+            if parity_c4 is not None:
+                line["c4"]["parity_check"] = parity_c4
         if world == 1 and not args.no_cpu_baseline and not args.heat:
             try:
                 b = cpu_run(dict(rows=args.rows, cols=args.cols, soil_layers=args.soil_layers, saturated_bottom=args.saturated_bottom),

@@ -17,8 +17,9 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
 
-def slab_parity(gpu, rank: int, world: int, *, heat: bool = False, nccl: bool = True, threads: int = 1) -> dict:
-    """48 x 40 x (1+5) storm (water) or 24 x 16 x (1+4) coupled heat, split into `world` row slabs, against the
+def slab_parity(gpu, rank: int, world: int, *, heat: bool = False, nccl: bool = True, threads: int = 1, c4: bool = False) -> dict:
+    """48 x 40 x (1+5) storm (water), 24 x 16 x (1+4) coupled heat, or (c4) the C4 recipe at small size -- 32 x 24 x (1+20)
+    with the lower third of the layers saturated and free drainage --, split into `world` row slabs, against the
     reference (oracle/_ref when it travelled with the snapshot, else the C restatement) run on the whole catchment
     by every rank.  Returns the comparison; raises nothing (ok False + reason instead)."""
     from criteria3d_b200 import BoundaryType, Field, SoilFluxes3D
@@ -26,9 +27,10 @@ def slab_parity(gpu, rank: int, world: int, *, heat: bool = False, nccl: bool = 
     from criteria3d_b200.synth import Catchment, run_hours, set_heat_forcing, setup
     from oracle import checker_path
 
-    R, C, L = (24, 16, 4) if heat else (48, 40, 5)
-    hours, max_steps = ([0.0, 10.0], 10) if heat else ([20.0, 40.0], 50)
-    slab, lc = setup_slab(gpu, R, C, L, rank, world, heat=heat, require_direct=not nccl)
+    R, C, L = (24, 16, 4) if heat else ((32, 24, 20) if c4 else (48, 40, 5))
+    hours, max_steps = ([0.0, 10.0], 10) if heat else (([40.0], 25) if c4 else ([20.0, 40.0], 50))
+    cat_kw = dict(saturated_bottom=True) if c4 else {}
+    slab, lc = setup_slab(gpu, R, C, L, rank, world, heat=heat, require_direct=not nccl, **cat_kw)
 
     def run(sf, cat):
         dts = []
@@ -39,11 +41,11 @@ def slab_parity(gpu, rank: int, world: int, *, heat: bool = False, nccl: bool = 
         return dts
     dts = run(gpu, lc)
     chk = SoilFluxes3D(checker_path())
-    cat = Catchment(R, C, L, heat=heat)
+    cat = Catchment(R, C, L, heat=heat, **cat_kw)
     setup(chk, cat, threads=threads)
     dts_ref = run(chk, cat)
 
-    out = {"world": world, "grid": f"{R}x{C}x(1+{L})" + (" coupled heat" if heat else ""), "checker": chk.backend,
+    out = {"world": world, "grid": f"{R}x{C}x(1+{L})" + (" coupled heat" if heat else "") + (" saturated lower third (C4 recipe)" if c4 else ""), "checker": chk.backend,
            "halo": getattr(gpu, "halo_mode", "?"), "steps": len(dts), "dt_sequence_equal": dts == dts_ref, "ok": True, "why": []}
     if dts != dts_ref:
         out["ok"] = False
@@ -145,7 +147,7 @@ def main():
         dist.destroy_process_group()
         sys.exit(0 if out["ok"] else 1)
     heat = "--heat" in sys.argv
-    out = reduce_over_ranks(slab_parity(gpu, rank, world, heat=heat, nccl=not share))
+    out = reduce_over_ranks(slab_parity(gpu, rank, world, heat=heat, nccl=not share, c4="--c4" in sys.argv))
     dist.barrier()
     if rank == 0:
         print(f"[mgpu_slab_check] {'ok' if out['ok'] else 'FAILED'}: {out}", flush=True)

@@ -64,3 +64,22 @@ def test_product_matches_oracle_codes(product, checker):
     a = contract_codes(product)
     b = contract_codes(checker)
     assert np.array_equal(a, b, equal_nan=True), (np.where(a != b), a[a != b], b[a != b])
+
+
+@pytest.mark.parametrize("lib", [ORACLE_LIB, REFERENCE_LIB], ids=["oracle", "reference"])
+def test_async_layer_rasters_on_the_cpu_libraries_are_the_synchronous_call(lib):
+    """sf3d_ext_get_layer_rasters_async / sf3d_ext_wait_rasters exist in every implementation of the ABI; the CPU
+    libraries have nothing to overlap and return the same maps at once"""
+    if not lib.exists():
+        pytest.skip(f"{lib.name} not built")
+    sf = SoilFluxes3D(lib)
+    cat = Catchment(7, 6, 3)
+    setup(sf, cat, threads=1)
+    shape = (cat.rows, cat.cols)
+    want = sf.get_layer_rasters(Field.MATRIC_POTENTIAL, 0, cat.layers, shape)
+    got = np.empty_like(want)
+    sf.get_layer_rasters_async(Field.MATRIC_POTENTIAL, 0, cat.layers, shape, got)
+    sf.wait_rasters()
+    assert np.array_equal(got, want)
+    with pytest.raises(RuntimeError):
+        sf.get_layer_rasters_async(Field.MATRIC_POTENTIAL, cat.layers, 1, shape, got[:1])      # layer out of range
