@@ -32,7 +32,8 @@
 #endif
 constexpr int kHeatLinkUnroll = SF3D_HEAT_LINK_UNROLL;
 #ifndef SF3D_THERMAL_UNROLL
-#define SF3D_THERMAL_UNROLL 2        // link loop of the thermal invariant fluxes
+#define SF3D_THERMAL_UNROLL 5        // link loops of the thermal invariant fluxes: two groups of five links (A/B on B200, two-pass form:
+                                     // unroll 1 / 2 / 5 / 10 -> 2.01 / 1.80 / 1.59 / 1.71 ms per approximation for this pass + the assembly)
 #endif
 constexpr int kThermalUnroll = SF3D_THERMAL_UNROLL;
 
@@ -390,6 +391,29 @@ SF3D_HD void sf3d_row_thermal_invariant(const SF3DView &v, uint32_t i)
 {
     if (i < v.Ns) return;
     const int32_t *off = sf3d_row_pattern(v, i);
+#ifdef SF3D_DEVICE_MATH
+    // Two passes over the links, one per conductivity (liquid, then vapour): each keeps ONE operand pair per link end live.
+    // The single-pass form spilled at the 32 registers this kernel runs best with (ncu: 12 % of the stall samples on the
+    // spill stores, LSU throttling on top); the second pass re-reads the linked temperatures and the link geometry from L1.
+    // The sum is taken liquid links first, then vapour links (a rounding-level reordering of the reference's per-link sums).
+    const double tmi = v.hTm[i];
+    double invariant = 0.;
+    const int nPass = v.computeHeatVapor ? 2 : 1;
+    for (int pass = 0; pass < nPass; ++pass)
+    {
+        const double *op = pass ? v.hTVK : v.hTLK;              // vapour pairs are stored / rho_w (sf3d_heat_node_water)
+        const SF3DPair ai = h_pair_load(op, i);
+        #pragma unroll kThermalUnroll
+        for (int c = 0; c < SF3D_NLINK; ++c)
+        {
+            const uint32_t j = sf3d_col_index(v, off, i, c);
+            if (j == i || j < v.Ns) continue;                   // absent link, or the infiltration link of the first soil layer
+            const double zeta = h_link_zeta(v, i, sf3d_slot_of_col(c));
+            invariant += (h_pair_mean(ai, h_pair_load(op, j)) * (v.hTm[j] - tmi)) * zeta;
+        }
+    }
+    v.hInv[i] = invariant;
+#else
     const SF3DPair tli = h_pair_load(v.hTLK, i);
     SF3DPair tvi = {0., 0.};
     if (v.computeHeatVapor) tvi = h_pair_load(v.hTVK, i);
@@ -405,6 +429,7 @@ SF3D_HD void sf3d_row_thermal_invariant(const SF3DView &v, uint32_t i)
         invariant += sf3d_heat_thermal_invariant(v, i, sf3d_slot_of_col(c), tli, tvi, tmi, h_pair_load(v.hTLK, j), tvj, v.hTm[j]);
     }
     v.hInv[i] = invariant;
+#endif
 }
 
 // computeNodeAtmosphericLatentVaporFlux (heat.cpp:988-1007), node = HeatSurface soil node
