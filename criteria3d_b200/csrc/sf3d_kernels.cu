@@ -1043,8 +1043,8 @@ __global__ void __launch_bounds__(SF3D_BLOCK, SF3D_HEAT_BLOCKS) kern_heat_begin(
     {
         sf3d_row_heat_begin(v, i, dtHeat, dtWater);
         // resetFluxValues(true, false) (heat.cpp:55-78)
-        if (v.hfSaveMode == 1) { for (int s = 0; s < SF3D_NLINK; ++s) v.lfluxes[(size_t)s * N + i] = SF3D_NODATA; }
-        else if (v.hfSaveMode == 2)
+        // (save mode Total: the HeatTotal slots are reset by the heat assembly's own store, see sf3d_row_heat_assemble)
+        if (v.hfSaveMode == 2)
             for (int t = 0; t < 5; ++t) for (int s = 0; s < SF3D_NLINK; ++s) v.lfluxes[((size_t)t * SF3D_NLINK + s) * N + i] = SF3D_NODATA;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0)

@@ -36,6 +36,10 @@ constexpr int kHeatLinkUnroll = SF3D_HEAT_LINK_UNROLL;
                                      // unroll 1 / 2 / 5 / 10 -> 2.01 / 1.80 / 1.59 / 1.71 ms per approximation for this pass + the assembly)
 #endif
 constexpr int kThermalUnroll = SF3D_THERMAL_UNROLL;
+#ifndef SF3D_HEAT_ACCEPT_UNROLL
+#define SF3D_HEAT_ACCEPT_UNROLL 1    // link loop of saveNodeHeatFluxes
+#endif
+constexpr int kHeatAcceptUnroll = SF3D_HEAT_ACCEPT_UNROLL;
 
 // pow() with the small integer exponents heat.cpp passes: the product multiplies, the reference-rounding
 // build calls the library like the reference does
@@ -275,6 +279,15 @@ SF3D_HD double h_psi_avg(const SF3DView &v, uint32_t j, double dtHeat, double dt
 #else
     return (h_H_from_steps(v, j, dtHeat, dtWater) + v.oldH[j]) * 0.5 - v.z[j];
 #endif
+}
+
+// linked node of a slot without the dependent 4-byte load of the link index array: from the row's link pattern (kernel
+// parameters / the small pattern table) like the sweeps; the explicit matrix column array when patterns are off; the link
+// index array on host views
+SF3D_HD uint32_t h_link_node(const SF3DView &v, const int32_t *off, uint32_t i, int slot)
+{
+    if (off || v.mcol) return sf3d_col_index(v, off, i, sf3d_col_of_slot(slot));
+    return v.lidx[(size_t)slot * v.N + i];
 }
 
 // ---- water-side hooks --------------------------------------------------------------------------
@@ -555,12 +568,13 @@ SF3D_HD void sf3d_row_save_water_fluxes(const SF3DView &v, uint32_t i, double dt
 {
     const size_t N = v.N;
     const uint32_t m = v.meta[i];
+    const int32_t *off = sf3d_row_pattern(v, i);
     #pragma unroll kHeatLinkUnroll
     for (int slot = 0; slot < SF3D_NLINK; ++slot)
     {
         if (!META_HAS_SLOT(m, slot)) continue;
         const size_t li = (size_t)slot * N + i;
-        const uint32_t j = v.lidx[li];
+        const uint32_t j = h_link_node(v, off, i, slot);
         const double srcAvgH = h_Hs(v, i, dtHeat, dtWater);
         const double dstAvgH = h_Hs(v, j, dtHeat, dtWater);
         const double A = v.mval[(size_t)sf3d_col_of_slot(slot) * N + i];      // normalised entry x 1.0 (Q1); 0 if not stored (Q2)
@@ -699,10 +713,17 @@ SF3D_HD double h_advective_flux(const SF3DView &v, uint32_t i, int slot, uint32_
 SF3D_HD void sf3d_row_heat_assemble(const SF3DView &v, uint32_t i, double dtHeat, double dtWater)
 {
     const size_t N = v.N;
+    // save mode Total: this pass writes the HeatTotal slot of EVERY link (the value or NODATA), which is the reset of
+    // resetFluxValues(true, false) (heat.cpp:55-78) and the first saveNodeHeatSpecificFlux in one store, without a read
+    const bool totalOnly = v.hfSaveMode == 1;
     if (i < v.Ns)
     {
         #pragma unroll 1
-        for (int s = 0; s < SF3D_NLINK; ++s) v.mval[(size_t)s * N + i] = 0.;
+        for (int s = 0; s < SF3D_NLINK; ++s)
+        {
+            v.mval[(size_t)s * N + i] = 0.;
+            if (totalOnly) v.lfluxes[(size_t)s * N + i] = SF3D_NODATA;
+        }
         v.hdiag[i] = 0.;
         v.b[i] = v.T[i];
         return;
@@ -734,27 +755,39 @@ SF3D_HD void sf3d_row_heat_assemble(const SF3DView &v, uint32_t i, double dtHeat
     const double wf = v.heatWF;
     double sumDP = 0., sumF0 = 0., invariant = 0.;
     double val[SF3D_NLINK];
+    const int32_t *off = sf3d_row_pattern(v, i);
     #pragma unroll kHeatLinkUnroll
     for (int slot = 0; slot < SF3D_NLINK; ++slot)
     {
         val[slot] = 0.;
-        if (!META_HAS_SLOT(m, slot)) continue;
-        const uint32_t j = v.lidx[(size_t)slot * N + i];
-        if (j < v.Ns) continue;                                    // !isHeatNode(linked), heat.cpp:423
+        const uint32_t j = META_HAS_SLOT(m, slot) ? h_link_node(v, off, i, slot) : 0u;
+        if (!META_HAS_SLOT(m, slot) || j < v.Ns)                    // absent link / !isHeatNode(linked), heat.cpp:423
+        {
+            if (totalOnly) v.lfluxes[(size_t)slot * N + i] = SF3D_NODATA;
+            continue;
+        }
         const double e = h_conduction(v, i, slot, j, dtHeat, dtWater);
         double latent = 0., advective = 0.;
+        double total = SF3D_NODATA;                                 // saveNodeHeatSpecificFlux on a freshly reset slot
         if (v.computeHeatVapor)
         {
             // computeIsothermalLatentHeatFlux (heat.cpp:590-600)
             const double avgLambda = (h_latent_vaporization(v.T[i] - HC_ZEROCELSIUS) + h_latent_vaporization(v.T[j] - HC_ZEROCELSIUS)) * 0.5;
             latent = avgLambda * h_isothermal_vapor_flux(v, i, slot, j, dtHeat, dtWater);
-            h_save_specific_flux(v, i, slot, 2, latent);
+            if (totalOnly) total = (double)(float)latent;
+            else h_save_specific_flux(v, i, slot, 2, latent);
         }
         if (v.computeHeatAdvection)
         {
             advective = h_advective_flux(v, i, slot, j);
-            h_save_specific_flux(v, i, slot, 4, advective);
+            if (totalOnly)
+            {
+                const double a = (double)(float)advective;
+                total = (double)(float)((total == SF3D_NODATA) ? a : total + a);
+            }
+            else h_save_specific_flux(v, i, slot, 4, advective);
         }
+        if (totalOnly) v.lfluxes[(size_t)slot * N + i] = total;
         invariant += advective + latent;
         // cpusolver.cpp:545-552
         sumDP += e * wf;
@@ -841,11 +874,12 @@ SF3D_HD void sf3d_row_heat_accept(const SF3DView &v, uint32_t i, double dtHeat, 
     if (v.hfSaveMode != 0)
     {
         const uint32_t m = v.meta[i];
-        #pragma unroll 1
+        const int32_t *off = sf3d_row_pattern(v, i);
+        #pragma unroll kHeatAcceptUnroll
         for (int slot = 0; slot < SF3D_NLINK; ++slot)
         {
             if (!META_HAS_SLOT(m, slot)) continue;
-            const uint32_t j = v.lidx[(size_t)slot * N + i];
+            const uint32_t j = h_link_node(v, off, i, slot);
             if (j < v.Ns) continue;
             const double mv = v.mval[(size_t)slot * N + i] * v.hdiag[i];     // getMatrixElement: value x diagonal (kept for heat)
             double heatDiff = mv * (v.T[i] - v.T[j]) * v.heatWF + mv * (v.oldT[i] - v.oldT[j]) * (1. - v.heatWF);
