@@ -290,6 +290,10 @@ void release_all()
     dev_free(S.ctrl); S.ctrl = nullptr;
     dev_free(S.rasterRank); S.rasterRank = nullptr; S.raster = RasterDev{};
     dev_free(S.rasterStage); S.rasterStage = nullptr; S.rasterStageBytes = 0;
+    // overlapped map downloads still in flight read these buffers: wait for them first (a device error here is left to the
+    // next call that touches the device)
+    try { overlap_sync(); } catch (const DeviceError &) {}
+    for (int k = 0; k < 2; ++k) { dev_free(S.overlapStage[k]); S.overlapStage[k] = nullptr; S.overlapStageBytes[k] = 0; }
 }
 
 void *raster_stage(size_t bytes)
