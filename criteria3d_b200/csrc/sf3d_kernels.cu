@@ -1012,7 +1012,7 @@ __global__ void __launch_bounds__(SF3D_BLOCK, SF3D_HEAT_BLOCKS) kern_heat_coeffs
 __global__ void __launch_bounds__(SF3D_BLOCK, SF3D_HEAT_BLOCKS) kern_save_water_fluxes(SF3DView v, double dtHeat, double dtWater)
 {
     for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
-        sf3d_row_save_water_fluxes(v, i, dtHeat, dtWater);
+        if (!(v.world > 1 && META_GHOST(v.meta[i]))) sf3d_row_save_water_fluxes(v, i, dtHeat, dtWater);    // a ghost row has no link pattern
 }
 // updateBoundaryHeatData: heat flux per node + max heat-boundary Courant (heat.cpp:237-340)
 __global__ void __launch_bounds__(SF3D_BLOCK, SF3D_HEAT_BLOCKS) kern_boundary_heat(SF3DView v, double maxTimeStep, CommDev cm)
