@@ -25,12 +25,12 @@ def wire_ranks(sf: SoilFluxes3D, rank: int, world: int, device: torch.device | N
 
 
 def setup_slab(sf: SoilFluxes3D, rows: int, cols: int, n_soil_layers: int, rank: int, world: int,
-               numerics=None, require_direct: bool = False, **cat_kw) -> tuple[Slab, Catchment]:
+               numerics=None, require_direct: bool = False, heat_flux_mode: int | None = None, **cat_kw) -> tuple[Slab, Catchment]:
     """initialize3DModel's sequence on this rank's slab (owned rows + ghost rows), then the halo lists.
     The balance is initialised after the ghosts are known so that storage counts owned nodes only."""
     slab = make_slab(rows, cols, n_soil_layers, world, rank)
     cat = slab_catchment(slab, **cat_kw)
-    setup(sf, cat, numerics=numerics, balance=(world == 1))
+    setup(sf, cat, numerics=numerics, heat_flux_mode=heat_flux_mode, balance=(world == 1))
     if world > 1:
         peers, send, recv = slab.halo()
         _ok(sf.set_halo(peers, send, recv, slab.n_global), "sf3d_ext_set_halo")

@@ -17,7 +17,8 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
 
-def slab_parity(gpu, rank: int, world: int, *, heat: bool = False, nccl: bool = True, threads: int = 1, c4: bool = False) -> dict:
+def slab_parity(gpu, rank: int, world: int, *, heat: bool = False, nccl: bool = True, threads: int = 1, c4: bool = False,
+                save_all: bool = False) -> dict:
     """48 x 40 x (1+5) storm (water), 24 x 16 x (1+4) coupled heat, or (c4) the C4 recipe at small size -- 32 x 24 x (1+20)
     with the lower third of the layers saturated and free drainage --, split into `world` row slabs, against the
     reference (oracle/_ref when it travelled with the snapshot, else the C restatement) run on the whole catchment
@@ -30,7 +31,9 @@ def slab_parity(gpu, rank: int, world: int, *, heat: bool = False, nccl: bool = 
     R, C, L = (24, 16, 4) if heat else ((32, 24, 20) if c4 else (48, 40, 5))
     hours, max_steps = ([0.0, 10.0], 10) if heat else (([40.0], 25) if c4 else ([20.0, 40.0], 50))
     cat_kw = dict(saturated_bottom=True) if c4 else {}
-    slab, lc = setup_slab(gpu, R, C, L, rank, world, heat=heat, require_direct=not nccl, **cat_kw)
+    # save_all: heat flux save mode All (every flux type kept per link), which also runs the water-flux snapshot pass
+    hf_mode = 2 if (heat and save_all) else None
+    slab, lc = setup_slab(gpu, R, C, L, rank, world, heat=heat, require_direct=not nccl, heat_flux_mode=hf_mode, **cat_kw)
 
     def run(sf, cat):
         dts = []
@@ -42,10 +45,10 @@ def slab_parity(gpu, rank: int, world: int, *, heat: bool = False, nccl: bool = 
     dts = run(gpu, lc)
     chk = SoilFluxes3D(checker_path())
     cat = Catchment(R, C, L, heat=heat, **cat_kw)
-    setup(chk, cat, threads=threads)
+    setup(chk, cat, threads=threads, heat_flux_mode=hf_mode)
     dts_ref = run(chk, cat)
 
-    out = {"world": world, "grid": f"{R}x{C}x(1+{L})" + (" coupled heat" if heat else "") + (" saturated lower third (C4 recipe)" if c4 else ""), "checker": chk.backend,
+    out = {"world": world, "grid": f"{R}x{C}x(1+{L})" + (" coupled heat" if heat else "") + (", save mode All" if hf_mode else "") + (" saturated lower third (C4 recipe)" if c4 else ""), "checker": chk.backend,
            "halo": getattr(gpu, "halo_mode", "?"), "steps": len(dts), "dt_sequence_equal": dts == dts_ref, "ok": True, "why": []}
     if dts != dts_ref:
         out["ok"] = False
@@ -65,6 +68,19 @@ def slab_parity(gpu, rank: int, world: int, *, heat: bool = False, nccl: bool = 
         if not err <= tol:
             out["ok"] = False
             out["why"].append(f"{f.name} err {err:.3e} > {tol}")
+    if hf_mode:
+        # the water-flux snapshot of the heat step (flux types 5..8 of types.h:199, float-rounded), Down direction, on a
+        # sample of owned soil nodes: computed by a pass of its own that only runs in this save mode / with advection
+        owned_soil = np.flatnonzero(own & (np.arange(lc.n_nodes) >= lc.n_surface))
+        pick = owned_soil[:: max(1, owned_soil.size // 40)]
+        a = np.array([[gpu.getNodeHeatMaxFlux(int(i), 2, t) for t in range(5, 9)] for i in pick])
+        b = np.array([[chk.getNodeHeatMaxFlux(int(l2g[i]), 2, t) for t in range(5, 9)] for i in pick])
+        scale = np.maximum(np.abs(b), 1e-12 + 1e-6 * np.max(np.abs(b)))
+        err = float(np.max(np.abs(a - b) / scale))
+        out["max_dWaterFluxSnapshot_rel"] = err
+        if not (err <= 1e-4 and np.any(b != 0)):          # float-rounded values of differences of nearly equal heads
+            out["ok"] = False
+            out["why"].append(f"water flux snapshot err {err:.3e}")
     tw, tw_ref = gpu.getTotalWaterContent(), chk.getTotalWaterContent()
     out["total_water_rel"] = abs(tw - tw_ref) / abs(tw_ref)
     if not out["total_water_rel"] <= 1e-9:
@@ -147,7 +163,7 @@ def main():
         dist.destroy_process_group()
         sys.exit(0 if out["ok"] else 1)
     heat = "--heat" in sys.argv
-    out = reduce_over_ranks(slab_parity(gpu, rank, world, heat=heat, nccl=not share, c4="--c4" in sys.argv))
+    out = reduce_over_ranks(slab_parity(gpu, rank, world, heat=heat, nccl=not share, c4="--c4" in sys.argv, save_all="--save-all" in sys.argv))
     dist.barrier()
     if rank == 0:
         print(f"[mgpu_slab_check] {'ok' if out['ok'] else 'FAILED'}: {out}", flush=True)

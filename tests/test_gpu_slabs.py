@@ -25,11 +25,11 @@ def _torchrun(world, port, *args, env_extra=None, timeout=900):
     return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
 
 
-@pytest.mark.parametrize("world,heat", [(2, False), (4, False), (8, False), (2, True), (4, True), (4, "c4")])
+@pytest.mark.parametrize("world,heat", [(2, False), (4, False), (8, False), (2, True), (4, True), (4, "c4"), (2, "heat-all")])
 def test_slabs_match_oracle(world, heat):
     """water storm, coupled heat, and the C4 recipe (20 soil layers, saturated lower third, free drainage) at small size"""
-    args = ["--c4"] if heat == "c4" else (["--heat"] if heat else [])
-    r = _torchrun(world, 29600 + world + (20 if heat == "c4" else (10 if heat else 0)), *args)
+    args = {"c4": ["--c4"], "heat-all": ["--heat", "--save-all"]}.get(heat, ["--heat"] if heat else [])
+    r = _torchrun(world, 29600 + world + {"c4": 20, "heat-all": 30}.get(heat, 10 if heat else 0), *args)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "[mgpu_slab_check] ok" in r.stdout
     print(r.stdout.strip().splitlines()[-1])
