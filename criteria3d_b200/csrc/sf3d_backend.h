@@ -68,6 +68,8 @@ void k_node_phase(const SF3DView &v, double dt, int withCapacity);
 void k_assemble(const SF3DView &v, double dt, int approx, double dtMin);
 void k_jacobi(const SF3DView &v, const double *xin, double *xout, int maxIter, double tol);
 void k_post(const SF3DView &v, const double *x, double dt, int mode);
+bool k_post_can_follow_solve(const SF3DView &v);   // post pass enqueued behind the sweeps: one control read per approximation
+void k_post_follow_solve(const SF3DView &v, int start, double dt, double dtMin);
 void k_accept(const SF3DView &v, double dt, bool prepareNextTry);
 void k_restore_best(const SF3DView &v);
 void k_total_boundary_flow(const SF3DView &v, uint32_t boundaryType);

@@ -242,7 +242,7 @@ bool Engine::courantFailed(double /*deltaT*/, double courant)
 
 // CPUSolver::solveLinearSystem (cpusolver.cpp:672-703): the stopping rule runs on the device;
 // sweeps are enqueued in batches and the control block is read back once per batch.
-int Engine::solveWater(int approx)
+int Engine::solveWater(int approx, double deltaT, Ctrl *seen, bool *postDone)
 {
     Range r("sf3d water solve (Jacobi sweeps)");
     const int maxIter = (int)calcCurrentMaxIterationNumber(approx);
@@ -250,10 +250,14 @@ int Engine::solveWater(int approx)
     int launched = 0;
     Ctrl c{};
     int batch = std::min(std::max(lastSweeps + 1, 4), 32);
+    // the post pass rides behind the sweeps and decides on the device whether it runs (kern_post mode 3): the control
+    // block read that ends the solve then also carries the balance sums
+    const bool follow = k_post_can_follow_solve(v);
     if (k_jacobi_persistent_ok(v))
     {
         // small graph: the whole solve is one launch and one control-block read
         k_jacobi_persistent(v, xbuf(start), xbuf(start ^ 1), maxIter, p->residualTolerance);
+        if (follow) k_post_follow_solve(v, start, deltaT, p->deltaTmin);
         read_ctrl(v, &c);
     }
     else for (;;)
@@ -261,10 +265,15 @@ int Engine::solveWater(int approx)
         const int n = std::min(batch, maxIter - launched);
         for (int k = 0; k < n; ++k, ++launched)
             k_jacobi(v, xbuf((start + launched) & 1), xbuf((start + launched + 1) & 1), maxIter, p->residualTolerance);
+        if (follow) k_post_follow_solve(v, start, deltaT, p->deltaTmin);
         read_ctrl(v, &c);
         if (c.status != SOLVE_RUNNING || launched >= maxIter) break;
         batch = std::min(batch * 2, 32);
     }
+    const bool goesOn = c.status == SOLVE_CONVERGED || c.status == SOLVE_MAXITER
+                        || (c.status == SOLVE_DIVERGED && !(deltaT > p->deltaTmin));
+    *postDone = follow && goesOn;
+    *seen = c;
     if (c.status != SOLVE_COURANT_FAIL)
     {
         xcur = (start + c.sweeps) & 1;
@@ -287,7 +296,9 @@ BalanceResult Engine::waterApproximationLoop(double deltaT)
         Range r("sf3d water approximation");
         k_node_phase(v, deltaT, 1);                             // computeCapacity + updateBoundaryWaterData
         k_assemble(v, deltaT, approxIdx, p->deltaTmin);         // rows + Courant + normalisation
-        const int status = solveWater(approxIdx);
+        Ctrl seen{};
+        bool postDone = false;
+        const int status = solveWater(approxIdx, deltaT, &seen, &postDone);
 
         if (status == SOLVE_COURANT_FAIL)
         {
@@ -301,8 +312,8 @@ BalanceResult Engine::waterApproximationLoop(double deltaT)
             return BalanceResult::Halved;
         }
 
-        k_post(v, xbuf(xcur), deltaT, 0);                       // H = x ; Se ; storage ; sink sum
-        balanceResult = evaluateWaterBalance(approxIdx, deltaT);
+        if (!postDone) k_post(v, xbuf(xcur), deltaT, 0);        // H = x ; Se ; storage ; sink sum
+        balanceResult = evaluateWaterBalance(approxIdx, deltaT, postDone ? &seen : nullptr);
 
         if (balanceResult == BalanceResult::Accepted || balanceResult == BalanceResult::Halved
             || balanceResult == BalanceResult::Nan)
@@ -332,10 +343,11 @@ void Engine::computeCurrentMassBalance(double deltaT, const Ctrl &c)
 }
 
 // Water::evaluateWaterBalance (water.cpp:165-227)
-BalanceResult Engine::evaluateWaterBalance(int approxNr, double deltaT)
+BalanceResult Engine::evaluateWaterBalance(int approxNr, double deltaT, const Ctrl *seen)
 {
     Ctrl c{};
-    read_ctrl(v, &c);
+    if (seen) c = *seen;                    // the post pass followed the solve: its sums came with the solve's control read
+    else read_ctrl(v, &c);
     computeCurrentMassBalance(deltaT, c);
 
     const double currMBRerror = fabs(curStep.waterMBR);

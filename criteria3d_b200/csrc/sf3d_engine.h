@@ -45,9 +45,9 @@ struct Engine {
     // water
     bool          waterMainLoop(double maxTimeStep, double &acceptedTimeStep);
     BalanceResult waterApproximationLoop(double deltaT);
-    int           solveWater(int approx);                    // returns final SOLVE_* status
+    int           solveWater(int approx, double deltaT, Ctrl *seen, bool *postDone);   // returns final SOLVE_* status
     bool          courantFailed(double deltaT, double courant);
-    BalanceResult evaluateWaterBalance(int approx, double deltaT);
+    BalanceResult evaluateWaterBalance(int approx, double deltaT, const Ctrl *seen = nullptr);
     void          computeCurrentMassBalance(double deltaT, const Ctrl &c);
     void          acceptStep(double deltaT);
     void          restoreBestStep(double deltaT);

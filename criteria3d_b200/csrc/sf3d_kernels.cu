@@ -772,8 +772,24 @@ __global__ void __launch_bounds__(SF3D_BLOCK) kern_unpack(double *__restrict__ x
 }
 
 // H = x, Se refresh, and the two mass-balance sums
-__global__ void __launch_bounds__(SF3D_BLOCK, SF3D_POST_BLOCKS) kern_post(SF3DView v, const double *__restrict__ x, double dt, int mode, CommDev cm)
+// mode 3 ("follow the solve"): enqueued right behind a batch of sweeps, before the host has seen how the solve ended.  The
+// kernel reads the outcome itself: it runs as mode 0 on the vector the last executed sweep wrote when the solve ended in a
+// state the host goes on from (converged / sweep cap / diverged at the minimum time step: waterApproximationLoop,
+// cpusolver.cpp:431-457), and returns at once otherwise (solve still running, Courant failure, divergence that halves the
+// step).  One control-block read then tells the host both how the solve ended and the balance sums.  x = x0, xAlt = x1,
+// start = index of the buffer that held the solution when the solve began; every block (and every rank: the status derives
+// from all-reduced values) takes the same branch.
+__global__ void __launch_bounds__(SF3D_BLOCK, SF3D_POST_BLOCKS) kern_post(SF3DView v, const double *__restrict__ x, double dt, int mode, CommDev cm,
+                                                                        const double *__restrict__ xAlt = nullptr, int start = 0, double dtMin = 0.)
 {
+    if (mode == 3)
+    {
+        const int st = v.ctrl->status;
+        const bool goesOn = st == SOLVE_CONVERGED || st == SOLVE_MAXITER || (st == SOLVE_DIVERGED && !(dt > dtMin));
+        if (!goesOn) return;
+        if ((start + v.ctrl->sweeps) & 1) x = xAlt;
+        mode = 0;
+    }
     __shared__ double sh[SF3D_BLOCK / 32];
     double storage = 0., sinkSum = 0.;
     for (uint32_t i = blockIdx.x * SF3D_BLOCK + threadIdx.x; i < v.N; i += gridDim.x * SF3D_BLOCK)
@@ -1593,6 +1609,19 @@ void k_post(const SF3DView &v, const double *x, double dt, int mode)
         comm_allreduce(v.ctrl->red, 2, false, v.ctrl);
         kern_rule_post<<<1, 1, 0, g_stream>>>(v.ctrl); LAUNCH_CHECK();
     }
+}
+// the post pass enqueued behind the sweeps (kern_post mode 3).  Not with the separately launched all-reduces of the NCCL /
+// separate-kernel forms (their reduction kernels would run on a skipped pass); SF3D_POST_FOLLOWS_SOLVE=0 switches it off
+bool k_post_can_follow_solve(const SF3DView &v)
+{
+    static const bool on = !(getenv("SF3D_POST_FOLLOWS_SOLVE") && atoi(getenv("SF3D_POST_FOLLOWS_SOLVE")) == 0);
+    return on && (v.world == 1 || comm_dev().mine != nullptr);
+}
+void k_post_follow_solve(const SF3DView &v, int start, double dt, double dtMin)
+{
+    const CommDev cm = comm_dev();
+    ProfScope ps(SF3D_K_POST);
+    kern_post<<<GRID(v.N)>>>(v, v.x0, dt, 3, cm, v.x1, start, dtMin); LAUNCH_CHECK();
 }
 void k_accept(const SF3DView &v, double dt, bool prepareNextTry)
 {
