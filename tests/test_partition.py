@@ -25,15 +25,17 @@ def test_slab_rows_cover_the_dem_once(rows, world):
     assert max(sizes) - min(sizes) <= 1
 
 
+@pytest.mark.parametrize("shape,kw", [((13, 9, 3), {}), ((12, 6, 20), {"saturated_bottom": True})], ids=["storm", "c4-recipe"])
 @pytest.mark.parametrize("world", [2, 3])
-def test_local_graph_equals_global_graph_on_owned_nodes(world):
+def test_local_graph_equals_global_graph_on_owned_nodes(world, shape, kw):
     """Build the whole catchment and every slab with the CPU oracle: for every OWNED node the link
-    slot table, mapped to global ids, and the geometry are identical to the global build."""
+    slot table, mapped to global ids, the geometry and the initial state (incl. the C4 recipe: 20 soil layers, lower third
+    saturated) are identical to the global build."""
     if not ORACLE_LIB.exists():
         pytest.skip("oracle library not built")
     sf = SoilFluxes3D(ORACLE_LIB)
-    R, C, L = 13, 9, 3
-    cat = Catchment(R, C, L)
+    R, C, L = shape
+    cat = Catchment(R, C, L, **kw)
     setup(sf, cat, threads=1)
     g_tab = [sf.link_table(s, 0, cat.n_nodes) for s in range(10)]
     g_meta = sf.node_meta(0, cat.n_nodes)
@@ -42,7 +44,7 @@ def test_local_graph_equals_global_graph_on_owned_nodes(world):
     owned_total = 0
     for rank in range(world):
         slab = make_slab(R, C, L, world, rank)
-        lc = slab_catchment(slab)
+        lc = slab_catchment(slab, **kw)
         setup(sf, lc, threads=1)
         l2g = slab.local_to_global()
         own = slab.owned_mask()
